@@ -1,0 +1,104 @@
+/*
+ * include/mmfs_b200.h -- C ABI of libmmfs_b200.so (hand-written sm_100a kernels for
+ * the MM-Interleaved interleaved image-text forward hot path).
+ *
+ * Plain pointers and sizes only: no torch / ATen types cross this boundary.  Every
+ * entry point returns MMFS_OK (0) or a negative status; the message for the calling
+ * thread's last failure is available from mmfs_last_error().  All kernels are
+ * enqueued asynchronously on the caller's stream (cudaStream_t passed as void*; NULL =
+ * the legacy default stream) and retain no references to their arguments, matching
+ * the reference op's contract (ops/src/cuda/ms_deform_attn_cuda.cu:66: current ATen
+ * stream, asynchronous return).  Unlike the reference, launch errors are returned to
+ * the caller rather than printf-ed (ops/src/cuda/ms_deform_im2col_cuda.cuh:951-955).
+ *
+ * The reference-side binding for each symbol is shown in INTEGRATION.md.
+ */
+#ifndef MMFS_B200_H_
+#define MMFS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMFS_B200_ABI_VERSION 1
+
+/* status codes */
+#define MMFS_OK            0
+#define MMFS_EINVAL       (-1) /* bad argument (null pointer, non-positive dim, ...)    */
+#define MMFS_EUNSUPPORTED (-2) /* shape / dtype outside what the kernels implement      */
+#define MMFS_ECUDA        (-3) /* CUDA runtime / launch error, text in mmfs_last_error() */
+
+/* element types (the reference dispatches double/float/half: cu:65; bf16 is a superset) */
+#define MMFS_F32  0
+#define MMFS_F16  1
+#define MMFS_BF16 2
+#define MMFS_F64  3
+
+/* flags for mmfs_msda_forward */
+#define MMFS_MSDA_STRICT 1u /* also fetch taps whose attention weight is exactly 0 (the
+                               reference multiplies them in, which only matters when
+                               `value` holds inf/nan); default skips those fetches */
+
+int mmfs_abi_version(void);
+const char *mmfs_last_error(void);
+
+/*
+ * Multi-scale deformable attention forward.
+ * Replaces ms_deform_attn_forward / ms_deform_attn_cuda_forward
+ *   (ops/src/ms_deform_attn.h:20-39, ops/src/cuda/ms_deform_attn_cuda.cu:21-81) and the
+ *   kernel + launcher ms_deformable_im2col_gpu_kernel / ms_deformable_im2col_cuda
+ *   (ops/src/cuda/ms_deform_im2col_cuda.cuh:240-302, 926-957).
+ *
+ *   value           (N, S, M, D)        dtype, device, contiguous
+ *   spatial_shapes  (L, 2) int64 [H,W]  DEVICE pointer (reference reads it on device, cu:68)
+ *   level_start     (L,)   int64        DEVICE pointer (cu:69)
+ *   sampling_loc    (N, Lq, M, L, P, 2) dtype, last dim (x, y) normalised to [0,1]
+ *   attn_weight     (N, Lq, M, L, P)    dtype
+ *   out             (N, Lq, M*D)        dtype; fully overwritten (no pre-zeroing needed;
+ *                                       the reference allocates it with at::zeros, cu:55)
+ * All N batch entries are processed by ONE launch (the reference launches N /
+ * im2col_step kernels, cu:62-76; im2col_step only partitions launches and does not
+ * change results, so it is not part of this ABI -- the Python shim validates it).
+ * Accumulation is fp32 for f32/f16/bf16 and fp64 for f64 (at::opmath_type, cuh:32),
+ * with one rounding to dtype at the store (cuh:300).
+ */
+int mmfs_msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start,
+                      const void *sampling_loc, const void *attn_weight, void *out,
+                      int N, int S, int M, int D, int L, int Lq, int P,
+                      int dtype, unsigned flags, void *stream);
+
+/*
+ * Integer index stream of the sampler, for parity checking of the sampling-point index
+ * math (same device function as the forward kernels use).  idx is int32
+ * (N, Lq, M, L, P, 8) = [in_range, h_low, w_low, valid_mask(bit k = corner k+1 fetched),
+ * ptr1, ptr2, ptr3, ptr4] with ptr_k the element offset of channel 0 relative to the level
+ * base exactly as cuh:50-80 computes it (-1 when the corner is not fetched; all-zero /
+ * -1 record when the point fails the in-range predicate of cuh:291).
+ */
+int mmfs_msda_index_stream(const int64_t *spatial_shapes, const int64_t *level_start,
+                           const void *sampling_loc, int32_t *idx,
+                           int N, int M, int D, int L, int Lq, int P,
+                           int dtype, void *stream);
+
+/*
+ * Same op through HOST buffers: copies the inputs host->device, runs
+ * mmfs_msda_forward, copies `out` back and synchronises the stream before returning.
+ * This is the end-to-end form a host-side caller of the reference plugin would use;
+ * spatial_shapes / level_start are HOST pointers here.  Device scratch is cached per
+ * thread and grown on demand; mmfs_release_scratch() frees it.
+ */
+int mmfs_msda_forward_host(const void *value, const int64_t *spatial_shapes, const int64_t *level_start,
+                           const void *sampling_loc, const void *attn_weight, void *out,
+                           int N, int S, int M, int D, int L, int Lq, int P,
+                           int dtype, unsigned flags, void *stream);
+void mmfs_release_scratch(void);
+
+/* Tuning knobs (benchmarks / tests only): warps per CTA (0 = automatic). */
+int mmfs_msda_set_tuning(int warps_per_cta, int mapping);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMFS_B200_H_ */

@@ -1,0 +1,16 @@
+"""mm_interleaved_b200 -- B200-native (sm_100a) kernels for MM-Interleaved's interleaved
+image-text forward hot path, behind the reference's own operator / module API.
+
+Import name ``mm_interleaved_b200`` (via the shim ``mm_interleaved_b200.py`` at the repo
+root); the directory carries the project's hyphenated name.
+"""
+from . import _lib  # noqa: F401
+from .msda import (  # noqa: F401
+    ms_deform_attn_backward,
+    ms_deform_attn_forward,
+    ms_deform_attn_forward_host,
+    msda_index_stream,
+)
+from .functions import MSDeformAttnFunction  # noqa: F401
+
+__version__ = "0.1.0"
