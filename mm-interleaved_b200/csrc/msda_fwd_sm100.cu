@@ -80,12 +80,12 @@ __device__ __forceinline__ bool corner_valid(int corner, int h_low, int w_low, i
 // ------------------------------------------------------------------------------------
 // Fast path: one warp per (b, q, m); D * sizeof(T) in {64,128,256,512} bytes.
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ void fma2(float &a0, float &a1, float w, float v0, float v1) {
+__device__ __forceinline__ void fma2(float &a0, float &a1, float w0, float w1, float v0, float v1) {
     // Blackwell packed fp32 FMA (fma.rn.f32x2): two accumulator updates per issue slot.
     unsigned long long acc, vv, ww;
     asm("mov.b64 %0, {%1, %2};" : "=l"(acc) : "f"(a0), "f"(a1));
     asm("mov.b64 %0, {%1, %2};" : "=l"(vv) : "f"(v0), "f"(v1));
-    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ww) : "f"(w0), "f"(w1));
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(ww), "l"(vv));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(acc));
 }
@@ -115,8 +115,18 @@ template <> struct PointLoad<__half> {
     }
 };
 
+// 512 bytes of zeros: taps that must not contribute (outside the map, invalid corner, masked
+// image) are pointed here with weight 0, so the gather loop needs no predicates and a
+// non-finite `value` entry can never leak through a 0 * inf product.
+__device__ uint4 g_zero_row[32];
+
+struct __align__(16) Tap {  // mailbox record handed from the index-math lane to the fetching slot
+    long long off;          // byte offset from this lane's value base (or to g_zero_row)
+    float w0, w1;           // lerp weight * attention weight, duplicated for fma.rn.f32x2
+};
+
 template <typename T, int D, bool SMEM_XCHG>
-__global__ void __launch_bounds__(512, 2)
+__global__ void __launch_bounds__(256, 3)
 msda_fwd_warp_kernel(const T *__restrict__ value, const int64_t *__restrict__ shapes,
                      const int64_t *__restrict__ starts, const T *__restrict__ loc,
                      const T *__restrict__ attn, T *__restrict__ out,
@@ -128,7 +138,7 @@ msda_fwd_warp_kernel(const T *__restrict__ value, const int64_t *__restrict__ sh
 
     extern __shared__ int4 s_dyn[];
     int4 *s_lvl = s_dyn;                                             // [L] {H, W, start, -}
-    uint2 *s_box = reinterpret_cast<uint2 *>(s_dyn + L);             // [warps][32] mailbox
+    Tap *s_box = reinterpret_cast<Tap *>(s_dyn + L);                 // [warps][2][32] mailbox
     for (int l = threadIdx.x; l < L; l += blockDim.x)
         s_lvl[l] = make_int4((int)shapes[2 * l], (int)shapes[2 * l + 1], (int)starts[l], 0);
     __syncthreads();
@@ -154,8 +164,15 @@ msda_fwd_warp_kernel(const T *__restrict__ value, const int64_t *__restrict__ sh
     const T *locp = loc + qm * (size_t)LP * 2;
     const T *attp = attn + qm * (size_t)LP;
     const int slot = lane / LPR;
+    // per-lane gather base, materialised in a register pair (one 64-bit add per fetch)
     const char *vbase = reinterpret_cast<const char *>(value + ((size_t)b * S * M + m) * D) + (lane % LPR) * 16;
-    const unsigned row_bytes = (unsigned)(M * D * (int)sizeof(T));
+    asm volatile("" : "+l"(vbase));
+    const long long row_bytes = (long long)M * D * (int)sizeof(T);
+    // what a lane in phase 1 must publish so that `vbase(of the fetching lane) + off` lands in
+    // g_zero_row: the fetching lane's (lane % LPR) * 16 is part of ITS vbase, so subtract the
+    // slab origin only.
+    const long long zero_off = reinterpret_cast<const char *>(g_zero_row) -
+                               reinterpret_cast<const char *>(value + ((size_t)b * S * M + m) * D);
     const bool strict = flags & MMFS_MSDA_STRICT;
 
     float acc[VEC];
@@ -165,6 +182,8 @@ msda_fwd_warp_kernel(const T *__restrict__ value, const int64_t *__restrict__ sh
     const int pt = lane >> 2, corner = lane & 3;  // phase-1 role: (point in chunk, corner)
     float nx = 0.f, ny = 0.f, na = 0.f;
     if (pt < LP) PointLoad<T>::load(locp, attp, pt, nx, ny, na);
+    Tap *box = s_box + warp * 64;
+    int parity = 0;
 
     for (int j0 = 0; j0 < LP; j0 += 8) {
         const float x = nx, y = ny, a = na;
@@ -172,57 +191,59 @@ msda_fwd_warp_kernel(const T *__restrict__ value, const int64_t *__restrict__ sh
         if (j + 8 < LP) PointLoad<T>::load(locp, attp, j + 8, nx, ny, na);  // software prefetch
 
         // ---- phase 1: one (point, corner) tap per lane ---------------------------------
-        int row = -1;
-        float wgt = 0.f;
+        Tap tap;
+        tap.off = zero_off;
+        tap.w0 = 0.f;
+        bool live = false;
         if (j < LP) {
             const int l = (p_shift >= 0) ? (j >> p_shift) : (j / P);
             const int4 lv = s_lvl[l];
             const PointGeom<float> g = point_geom(x, y, lv.x, lv.y);
-            if (g.in_range && corner_valid(corner, g.h_low, g.w_low, lv.x, lv.y) && (strict || a != 0.f)) {
+            live = g.in_range && corner_valid(corner, g.h_low, g.w_low, lv.x, lv.y) && (strict || a != 0.f);
+            if (live) {
                 const int hc = g.h_low + (corner >> 1), wc = g.w_low + (corner & 1);
-                row = lv.z + hc * lv.y + wc;  // row of the (S, M*D) slab of batch entry b
+                const int row = lv.z + hc * lv.y + wc;  // row of the (S, M*D) slab of batch entry b
+                tap.off = (long long)row * row_bytes;
                 const float fh = (corner & 2) ? g.lh : 1.f - g.lh;   // cuh:48, 83
                 const float fw = (corner & 1) ? g.lw : 1.f - g.lw;
-                wgt = fh * fw * a;
+                tap.w0 = fh * fw * a;
             }
         }
-        if (__ballot_sync(0xffffffffu, row >= 0) == 0u) continue;  // nothing to fetch (masked image)
+        tap.w1 = tap.w0;
+        if (__ballot_sync(0xffffffffu, live) == 0u) continue;  // nothing to fetch (masked image)
 
         // ---- phase 2: slot s fetches tap (it*RPI + s); 16 bytes per lane ---------------
+        Tap *mybox = box + parity * 32;   // double-buffered: one __syncwarp per chunk
+        parity ^= 1;
         if (SMEM_XCHG) {
-            __syncwarp();  // previous chunk's mailbox reads are done
-            s_box[warp * 32 + lane] = make_uint2((unsigned)row, __float_as_uint(wgt));
+            *reinterpret_cast<uint4 *>(mybox + lane) = *reinterpret_cast<const uint4 *>(&tap);  // STS.128
             __syncwarp();
         }
         constexpr int NIT = 32 / RPI;
-        constexpr int G = NIT < 8 ? NIT : 8;  // fetches in flight per lane
+        constexpr int G = NIT < 4 ? NIT : 4;  // fetches in flight per lane
 #pragma unroll
         for (int g0 = 0; g0 < NIT; g0 += G) {
-            int r[G];
-            float wt[G];
+            Tap t[G];
             uint4 v[G];
 #pragma unroll
             for (int it = 0; it < G; ++it) {
                 const int src = (g0 + it) * RPI + slot;
                 if (SMEM_XCHG) {
-                    const uint2 e = s_box[warp * 32 + src];
-                    r[it] = (int)e.x; wt[it] = __uint_as_float(e.y);
+                    *reinterpret_cast<uint4 *>(&t[it]) = *reinterpret_cast<const uint4 *>(mybox + src);  // LDS.128
                 } else {
-                    r[it] = __shfl_sync(0xffffffffu, row, src);
-                    wt[it] = __shfl_sync(0xffffffffu, wgt, src);
+                    t[it].off = __shfl_sync(0xffffffffu, tap.off, src);
+                    t[it].w0 = __shfl_sync(0xffffffffu, tap.w0, src);
+                    t[it].w1 = t[it].w0;
                 }
             }
 #pragma unroll
-            for (int it = 0; it < G; ++it) {
-                v[it] = make_uint4(0u, 0u, 0u, 0u);
-                if (r[it] >= 0) v[it] = ldg_nc_v4(vbase + (size_t)(unsigned)r[it] * row_bytes);
-            }
+            for (int it = 0; it < G; ++it) v[it] = ldg_nc_v4(vbase + t[it].off);
 #pragma unroll
             for (int it = 0; it < G; ++it) {
                 float f[VEC];
                 Vec16<T>::unpack(v[it], f);
 #pragma unroll
-                for (int k = 0; k < VEC; k += 2) fma2(acc[k], acc[k + 1], wt[it], f[k], f[k + 1]);
+                for (int k = 0; k < VEC; k += 2) fma2(acc[k], acc[k + 1], t[it].w0, t[it].w1, f[k], f[k + 1]);
             }
         }
     }
@@ -331,7 +352,7 @@ static int launch_warp(const void *value, const int64_t *shapes, const int64_t *
     int wpc = g_warps_per_cta;
     if (wpc <= 0) {
         const long want = 4L * num_sms();
-        wpc = 16;
+        wpc = 8;
         while (wpc > 1 && ((long)N * M * ((Lq + wpc - 1) / wpc) < want || wpc / 2 >= Lq)) wpc >>= 1;
     }
     const int mapping = g_mapping & 1;
@@ -339,7 +360,7 @@ static int launch_warp(const void *value, const int64_t *shapes, const int64_t *
     const long nrows = (long)N * Lq * M;
     const long nb = mapping == 0 ? (long)N * M * qtiles : (nrows + wpc - 1) / wpc;
     if (nb > 0x7fffffffL) { set_error("msda: grid too large (%ld CTAs)", nb); return MMFS_EUNSUPPORTED; }
-    const size_t smem = (size_t)L * sizeof(int4) + (X ? (size_t)wpc * 32 * sizeof(uint2) : 0);
+    const size_t smem = (size_t)L * sizeof(int4) + (X ? (size_t)wpc * 64 * sizeof(Tap) : 0);
     if (smem > 48 * 1024) { set_error("msda: too many levels (%d)", L); return MMFS_EUNSUPPORTED; }
     msda_fwd_warp_kernel<T, D, X><<<dim3((unsigned)nb), dim3(32 * wpc), smem, st>>>(
         (const T *)value, shapes, starts, (const T *)loc, (const T *)attn, (T *)out,
@@ -389,8 +410,8 @@ static int dispatch_d(const void *value, const int64_t *shapes, const int64_t *s
 using namespace mmfs;
 
 extern "C" int mmfs_msda_set_tuning(int warps_per_cta, int mapping) {
-    if (warps_per_cta < 0 || warps_per_cta > 16 || (warps_per_cta & (warps_per_cta - 1))) {
-        set_error("mmfs_msda_set_tuning: warps_per_cta must be 0 or a power of two <= 16");
+    if (warps_per_cta < 0 || warps_per_cta > 8 || (warps_per_cta & (warps_per_cta - 1))) {
+        set_error("mmfs_msda_set_tuning: warps_per_cta must be 0 or a power of two <= 8");
         return MMFS_EINVAL;
     }
     g_warps_per_cta = warps_per_cta;
