@@ -78,7 +78,8 @@ __device__ __forceinline__ bool corner_valid(int corner, int h_low, int w_low, i
 }
 
 // ------------------------------------------------------------------------------------
-// Fast path: one warp per (b, q, m); D * sizeof(T) in {64,128,256,512} bytes.
+// Fast path: persistent CTAs, one warp per output row (b, q, m) at a time;
+// D * sizeof(T) in {64,128,256,512} bytes.
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ void fma2(float &a0, float &a1, float w0, float w1, float v0, float v1) {
     // Blackwell packed fp32 FMA (fma.rn.f32x2): two accumulator updates per issue slot.
@@ -90,30 +91,29 @@ __device__ __forceinline__ void fma2(float &a0, float &a1, float w0, float w1, f
     asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(acc));
 }
 
-template <typename T> struct PointLoad;  // raw (x, y, a) of one sampling point -> fp32
-template <> struct PointLoad<float> {
-    __device__ __forceinline__ static void load(const float *locp, const float *attp, int j, float &x, float &y, float &a) {
-        const uint2 xy = ldg_stream_v2(locp + 2 * (size_t)j);
-        x = __uint_as_float(xy.x); y = __uint_as_float(xy.y);
-        a = __uint_as_float(ldg_stream_u32(attp + j));
-    }
-};
-template <> struct PointLoad<__nv_bfloat16> {
-    __device__ __forceinline__ static void load(const __nv_bfloat16 *locp, const __nv_bfloat16 *attp, int j, float &x, float &y, float &a) {
-        const uint32_t xy = ldg_stream_u32(locp + 2 * (size_t)j);
-        x = __uint_as_float(xy << 16); y = __uint_as_float(xy & 0xffff0000u);
-        a = __uint_as_float(((uint32_t)ldg_stream_u16(attp + j)) << 16);
-    }
-};
-template <> struct PointLoad<__half> {
-    __device__ __forceinline__ static void load(const __half *locp, const __half *attp, int j, float &x, float &y, float &a) {
-        const uint32_t xy = ldg_stream_u32(locp + 2 * (size_t)j);
-        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&xy));
-        x = f.x; y = f.y;
-        const uint16_t aw = ldg_stream_u16(attp + j);
-        a = __half2float(*reinterpret_cast<const __half *>(&aw));
-    }
-};
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// mbarrier + bulk async copy (TMA engine, SASS UBLKCP): one instruction stages a whole
+// sampling-location / attention-weight row of the next output row into shared memory.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                 "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 // 512 bytes of zeros: taps that must not contribute (outside the map, invalid corner, masked
 // image) are pointed here with weight 0, so the gather loop needs no predicates and a
@@ -121,141 +121,207 @@ template <> struct PointLoad<__half> {
 __device__ uint4 g_zero_row[32];
 
 struct __align__(16) Tap {  // mailbox record handed from the index-math lane to the fetching slot
-    long long off;          // byte offset from this lane's value base (or to g_zero_row)
+    long long off;          // byte offset from the head slab origin (or to g_zero_row)
     float w0, w1;           // lerp weight * attention weight, duplicated for fma.rn.f32x2
 };
 
-template <typename T, int D, bool SMEM_XCHG>
-__global__ void __launch_bounds__(256, 3)
-msda_fwd_warp_kernel(const T *__restrict__ value, const int64_t *__restrict__ shapes,
+template <typename T> __device__ __forceinline__ float elem_to_f32(const T *p);
+template <> __device__ __forceinline__ float elem_to_f32<float>(const float *p) { return *p; }
+template <> __device__ __forceinline__ float elem_to_f32<__half>(const __half *p) { return __half2float(*p); }
+template <> __device__ __forceinline__ float elem_to_f32<__nv_bfloat16>(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+
+constexpr int kTapStride = 33;                      // 16-byte units between corner planes (bank skew)
+constexpr int kTapsPerWarp = 4 * kTapStride;        // mailbox entries per warp (32 points x 4 corners)
+constexpr int kWarpsPerCta = 8;
+
+// Shared-memory layout of one CTA (all offsets 16-byte aligned):
+//   int4     lvl[L]                              {H, W, level_start, -}
+//   per warp: uint64_t bar[2]                    mbarriers of the two staging buffers
+//             T stage[2][stage_elems]            loc row (2*LP) then attn row (LP), padded to 16 B
+//             Tap taps[kTapsPerWarp]             mailbox
+template <typename T, int D>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, 3)
+msda_fwd_rows_kernel(const T *__restrict__ value, const int64_t *__restrict__ shapes,
                      const int64_t *__restrict__ starts, const T *__restrict__ loc,
                      const T *__restrict__ attn, T *__restrict__ out,
-                     long nrows, int S, int M, int L, int Lq, int P, int p_shift, unsigned flags, int qtiles, int mapping) {
+                     int S, int M, int L, int Lq, int P, int p_shift, unsigned flags,
+                     int rows_per_warp, int qtiles, long ntiles, int ctas_per_sm, int nsm,
+                     int stage_elems, int bulk_ok, int swizzle) {
     constexpr int VEC = 16 / (int)sizeof(T);  // channels per lane
     constexpr int LPR = D / VEC;              // lanes per value row
     constexpr int RPI = 32 / LPR;             // rows (taps) fetched per warp instruction
     static_assert(D % VEC == 0 && LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "unsupported D");
 
     extern __shared__ int4 s_dyn[];
-    int4 *s_lvl = s_dyn;                                             // [L] {H, W, start, -}
-    Tap *s_box = reinterpret_cast<Tap *>(s_dyn + L);                 // [warps][2][32] mailbox
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int4 *s_lvl = s_dyn;
+    const int per_warp_bytes = 16 + 2 * stage_elems * (int)sizeof(T) + kTapsPerWarp * (int)sizeof(Tap);
+    char *wbase = reinterpret_cast<char *>(s_dyn + L) + warp * per_warp_bytes;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wbase);
+    T *stage = reinterpret_cast<T *>(wbase + 16);
+    Tap *taps = reinterpret_cast<Tap *>(wbase + 16 + 2 * stage_elems * (int)sizeof(T));
+
     for (int l = threadIdx.x; l < L; l += blockDim.x)
         s_lvl[l] = make_int4((int)shapes[2 * l], (int)shapes[2 * l + 1], (int)starts[l], 0);
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    int b, m, q;
-    if (mapping == 0) {  // (b, m, q-tile): all warps of a CTA share one head slab
-        const int qt = blockIdx.x % qtiles;
-        const int bm = blockIdx.x / qtiles;
-        m = bm % M; b = bm / M;
-        q = qt * wpc + warp;
-    } else {             // reference-like order (b, q, m): for A/B measurements only
-        const long gw = (long)blockIdx.x * wpc + warp;
-        if (gw >= nrows) return;
-        m = (int)(gw % M);
-        const long bq = gw / M;
-        q = (int)(bq % Lq); b = (int)(bq / Lq);
-    }
-    if (q >= Lq) return;  // no block-level sync below this point
-
     const int LP = L * P;
-    const size_t qm = ((size_t)b * Lq + q) * M + m;
-    const T *locp = loc + qm * (size_t)LP * 2;
-    const T *attp = attn + qm * (size_t)LP;
-    const int slot = lane / LPR;
-    // per-lane gather base, materialised in a register pair (one 64-bit add per fetch)
-    const char *vbase = reinterpret_cast<const char *>(value + ((size_t)b * S * M + m) * D) + (lane % LPR) * 16;
-    asm volatile("" : "+l"(vbase));
     const long long row_bytes = (long long)M * D * (int)sizeof(T);
-    // what a lane in phase 1 must publish so that `vbase(of the fetching lane) + off` lands in
-    // g_zero_row: the fetching lane's (lane % LPR) * 16 is part of ITS vbase, so subtract the
-    // slab origin only.
-    const long long zero_off = reinterpret_cast<const char *>(g_zero_row) -
-                               reinterpret_cast<const char *>(value + ((size_t)b * S * M + m) * D);
     const bool strict = flags & MMFS_MSDA_STRICT;
+    const int slot = lane / LPR;
+    const uint32_t loc_bytes = (uint32_t)(2 * LP * (int)sizeof(T)), att_bytes = (uint32_t)(LP * (int)sizeof(T));
 
-    float acc[VEC];
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    // Work order.  A tile = kWarpsPerCta * rows_per_warp consecutive queries of ONE (b, m); tiles are
+    // numbered (b, m, q-tile) with the q-tile fastest.  CTA i of the persistent grid sits on SM
+    // (i % nsm) in the first (only) wave, so giving CTA i the tiles ((i % nsm) * ctas_per_sm +
+    // i / nsm) + k * grid makes all CTAs resident on one SM walk neighbouring q-tiles of the
+    // same head: the head's value slab stays L1-resident.
+    const long grid = gridDim.x;
+    long tile0 = blockIdx.x;
+    if (swizzle && grid == (long)nsm * ctas_per_sm) tile0 = (long)(blockIdx.x % nsm) * ctas_per_sm + blockIdx.x / nsm;
 
-    const int pt = lane >> 2, corner = lane & 3;  // phase-1 role: (point in chunk, corner)
-    float nx = 0.f, ny = 0.f, na = 0.f;
-    if (pt < LP) PointLoad<T>::load(locp, attp, pt, nx, ny, na);
-    Tap *box = s_box + warp * 64;
-    int parity = 0;
-
-    for (int j0 = 0; j0 < LP; j0 += 8) {
-        const float x = nx, y = ny, a = na;
-        const int j = j0 + pt;
-        if (j + 8 < LP) PointLoad<T>::load(locp, attp, j + 8, nx, ny, na);  // software prefetch
-
-        // ---- phase 1: one (point, corner) tap per lane ---------------------------------
-        Tap tap;
-        tap.off = zero_off;
-        tap.w0 = 0.f;
-        bool live = false;
-        if (j < LP) {
-            const int l = (p_shift >= 0) ? (j >> p_shift) : (j / P);
-            const int4 lv = s_lvl[l];
-            const PointGeom<float> g = point_geom(x, y, lv.x, lv.y);
-            live = g.in_range && corner_valid(corner, g.h_low, g.w_low, lv.x, lv.y) && (strict || a != 0.f);
-            if (live) {
-                const int hc = g.h_low + (corner >> 1), wc = g.w_low + (corner & 1);
-                const int row = lv.z + hc * lv.y + wc;  // row of the (S, M*D) slab of batch entry b
-                tap.off = (long long)row * row_bytes;
-                const float fh = (corner & 2) ? g.lh : 1.f - g.lh;   // cuh:48, 83
-                const float fw = (corner & 1) ? g.lw : 1.f - g.lw;
-                tap.w0 = fh * fw * a;
+    // Row sequence of this warp: rows r = 0..rows_per_warp-1 of tile, then tile += grid.  Rows past Lq
+    // (last q-tile) are skipped.  All 32-bit (host guarantees ntiles < 2^31).
+    struct Cursor { int tile, r, b, m, q; bool ok; };
+    const int itiles = (int)ntiles, igrid = (int)grid;
+    auto settle = [&](Cursor &c) {   // decode (tile, r) -> (b, m, q), skipping rows past Lq
+        for (;;) {
+            if (c.tile >= itiles) { c.ok = false; return; }
+            const int qt = c.tile % qtiles, bm = c.tile / qtiles;
+            c.m = bm % M; c.b = bm / M;
+            c.q = (qt * kWarpsPerCta + warp) * rows_per_warp + c.r;
+            if (c.q < Lq) { c.ok = true; return; }
+            c.r = 0; c.tile += igrid;  // the rest of this tile's rows are past Lq as well
+        }
+    };
+    auto advance = [&](Cursor c) -> Cursor {
+        if (++c.r == rows_per_warp) { c.r = 0; c.tile += igrid; }
+        settle(c);
+        return c;
+    };
+    auto stage_row = [&](int b, int m, int q, int buf) {  // whole warp calls; fills stage[buf]
+        const size_t qm = ((size_t)b * Lq + q) * M + m;
+        T *dst = stage + buf * stage_elems;
+        const T *lsrc = loc + qm * (size_t)LP * 2;
+        const T *asrc = attn + qm * (size_t)LP;
+        if (bulk_ok) {
+            if (lane == 0) {
+                mbar_expect_tx(&bar[buf], loc_bytes + att_bytes);
+                bulk_g2s(dst, lsrc, loc_bytes, &bar[buf]);
+                bulk_g2s(dst + 2 * LP, asrc, att_bytes, &bar[buf]);
             }
+        } else {  // rows not 16-byte aligned / sized: plain loads
+            for (int i = lane; i < 2 * LP; i += 32) dst[i] = lsrc[i];
+            for (int i = lane; i < LP; i += 32) dst[2 * LP + i] = asrc[i];
         }
-        tap.w1 = tap.w0;
-        if (__ballot_sync(0xffffffffu, live) == 0u) continue;  // nothing to fetch (masked image)
+    };
 
-        // ---- phase 2: slot s fetches tap (it*RPI + s); 16 bytes per lane ---------------
-        Tap *mybox = box + parity * 32;   // double-buffered: one __syncwarp per chunk
-        parity ^= 1;
-        if (SMEM_XCHG) {
-            *reinterpret_cast<uint4 *>(mybox + lane) = *reinterpret_cast<const uint4 *>(&tap);  // STS.128
-            __syncwarp();
-        }
-        constexpr int NIT = 32 / RPI;
-        constexpr int G = NIT < 4 ? NIT : 4;  // fetches in flight per lane
+    Cursor cur;
+    cur.tile = (int)tile0; cur.r = 0; cur.b = cur.m = cur.q = 0; cur.ok = false;
+    settle(cur);
+    unsigned n_staged = 0;  // rows staged so far: buffer = n & 1, parity = (n >> 1) & 1
+    if (cur.ok) stage_row(cur.b, cur.m, cur.q, 0);
+
+    while (cur.ok) {
+        // look ahead: next valid row of this warp, staged into the other buffer right away
+        const Cursor nxt = advance(cur);
+        const int b = cur.b, m = cur.m, q = cur.q;
+        const int buf = n_staged & 1;
+        const unsigned parity = (n_staged >> 1) & 1;
+        if (nxt.ok) stage_row(nxt.b, nxt.m, nxt.q, buf ^ 1);
+        if (bulk_ok) mbar_wait(&bar[buf], parity); else __syncwarp();
+        ++n_staged;
+
+        const T *s_loc = stage + buf * stage_elems;
+        const T *s_att = s_loc + 2 * LP;
+        const char *slab = reinterpret_cast<const char *>(value + ((size_t)b * S * M + m) * D);
+        const char *vbase = slab + (lane % LPR) * 16;   // per-lane gather base (one 64-bit add per fetch)
+        const long long zero_off = reinterpret_cast<const char *>(g_zero_row) - slab;
+
+        float acc[VEC];
 #pragma unroll
-        for (int g0 = 0; g0 < NIT; g0 += G) {
-            Tap t[G];
-            uint4 v[G];
+        for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+
+        for (int p0 = 0; p0 < LP; p0 += 32) {
+            // ---- phase 1: one sampling point per lane, four taps each ----------------------
+            const int j = p0 + lane;
+            Tap t4[4];
 #pragma unroll
-            for (int it = 0; it < G; ++it) {
-                const int src = (g0 + it) * RPI + slot;
-                if (SMEM_XCHG) {
-                    *reinterpret_cast<uint4 *>(&t[it]) = *reinterpret_cast<const uint4 *>(mybox + src);  // LDS.128
-                } else {
-                    t[it].off = __shfl_sync(0xffffffffu, tap.off, src);
-                    t[it].w0 = __shfl_sync(0xffffffffu, tap.w0, src);
-                    t[it].w1 = t[it].w0;
+            for (int k = 0; k < 4; ++k) { t4[k].off = zero_off; t4[k].w0 = 0.f; t4[k].w1 = 0.f; }
+            bool live = false;
+            if (j < LP) {
+                const float x = elem_to_f32(s_loc + 2 * j), y = elem_to_f32(s_loc + 2 * j + 1);
+                const float a = elem_to_f32(s_att + j);
+                const int l = (p_shift >= 0) ? (j >> p_shift) : (j / P);
+                const int4 lv = s_lvl[l];
+                const PointGeom<float> g = point_geom(x, y, lv.x, lv.y);
+                live = g.in_range && (strict || a != 0.f);
+                if (live) {
+                    const float hh = 1.f - g.lh, hw = 1.f - g.lw;                       // cuh:48
+                    const long long o00 = (long long)(lv.z + g.h_low * lv.y + g.w_low) * row_bytes;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (corner_valid(k, g.h_low, g.w_low, lv.x, lv.y)) {
+                            t4[k].off = o00 + ((k & 2) ? (long long)lv.y * row_bytes : 0ll) + ((k & 1) ? row_bytes : 0ll);
+                            const float wk = ((k & 2) ? g.lh : hh) * ((k & 1) ? g.lw : hw) * a;  // cuh:83
+                            t4[k].w0 = wk; t4[k].w1 = wk;
+                        }
+                    }
                 }
             }
+            const unsigned livemask = __ballot_sync(0xffffffffu, live);
+            if (livemask == 0u) continue;  // e.g. 32 points of masked images: nothing to fetch
+            __syncwarp();                  // previous pass finished reading the mailbox
 #pragma unroll
-            for (int it = 0; it < G; ++it) v[it] = ldg_nc_v4(vbase + t[it].off);
+            for (int k = 0; k < 4; ++k)    // corner planes skewed by one entry: conflict-free both ways
+                *reinterpret_cast<uint4 *>(&taps[k * kTapStride + lane]) = *reinterpret_cast<const uint4 *>(&t4[k]);
+            __syncwarp();
+
+            // ---- phase 2: slot s fetches tap (it*RPI + s) = (point, corner); 16 B per lane --
+            constexpr int NIT = 128 / RPI;                 // fetch instructions per pass
+            constexpr int G = NIT < 8 ? NIT : 8;           // fetches in flight per lane
+            constexpr int PPG = (G * RPI) / 4;             // points covered by one group
+#pragma unroll 1
+            for (int g0 = 0; g0 < NIT; g0 += G) {
+                const unsigned pm = (PPG >= 32) ? livemask : ((livemask >> ((g0 * RPI) / 4)) & ((1u << PPG) - 1u));
+                if (pm == 0u) continue;                    // warp-uniform: these points are all dead
+                Tap t[G];
+                uint4 v[G];
 #pragma unroll
-            for (int it = 0; it < G; ++it) {
-                float f[VEC];
-                Vec16<T>::unpack(v[it], f);
+                for (int it = 0; it < G; ++it) {
+                    const int tix = (g0 + it) * RPI + slot;        // tap index = point * 4 + corner
+                    *reinterpret_cast<uint4 *>(&t[it]) =
+                        *reinterpret_cast<const uint4 *>(&taps[(tix & 3) * kTapStride + (tix >> 2)]);
+                }
 #pragma unroll
-                for (int k = 0; k < VEC; k += 2) fma2(acc[k], acc[k + 1], t[it].w0, t[it].w1, f[k], f[k + 1]);
+                for (int it = 0; it < G; ++it) v[it] = ldg_nc_v4(vbase + t[it].off);
+#pragma unroll
+                for (int it = 0; it < G; ++it) {
+                    float f[VEC];
+                    Vec16<T>::unpack(v[it], f);
+#pragma unroll
+                    for (int k = 0; k < VEC; k += 2) fma2(acc[k], acc[k + 1], t[it].w0, t[it].w1, f[k], f[k + 1]);
+                }
             }
         }
-    }
 
-    // ---- epilogue: sum the RPI slots, one rounding, 16-byte stores ---------------------
+        // ---- epilogue: sum the RPI slots, one rounding, 16-byte stores ---------------------
 #pragma unroll
-    for (int off = LPR; off < 32; off <<= 1)
+        for (int off = LPR; off < 32; off <<= 1)
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
-    if (lane < LPR) {
-        T *op = out + qm * D + lane * VEC;
-        stg_v4(op, Vec16<T>::pack(acc));
+            for (int k = 0; k < VEC; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+        if (lane < LPR) {
+            const size_t qm = ((size_t)b * Lq + q) * M + m;
+            stg_v4(out + qm * D + lane * VEC, Vec16<T>::pack(acc));
+        }
+        __syncwarp();  // all lanes done with stage[buf] before it is refilled two rows later
+
+        cur = nxt;
     }
 }
 
@@ -338,33 +404,48 @@ msda_index_stream_kernel(const int64_t *__restrict__ shapes, const int64_t *__re
 // ------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------
-static int g_warps_per_cta = 0;  // 0 = automatic
-static int g_mapping = 0;        // bit0: 0 (b,m,q-tile) / 1 (b,q,m); bit1: shuffle exchange instead of mailbox
+static int g_rows_per_warp = 0;  // 0 = automatic
+static int g_mapping = 0;        // bit0: 1 = plain tile order (no per-SM swizzle)
 
-template <typename T, int D, bool X>
-static int launch_warp(const void *value, const int64_t *shapes, const int64_t *starts, const void *loc,
+template <typename T, int D>
+static int launch_rows(const void *value, const int64_t *shapes, const int64_t *starts, const void *loc,
                        const void *attn, void *out, int N, int S, int M, int L, int Lq, int P,
                        unsigned flags, cudaStream_t st) {
     int p_shift = -1;
     if ((P & (P - 1)) == 0) { p_shift = 0; while ((1 << p_shift) < P) ++p_shift; }
-    // warps per CTA: as large as possible (L1 locality on the head slab) while still giving
-    // every SM several CTAs; tiny problems (decode, Lq = 1) fall to 1-2 warps per CTA.
-    int wpc = g_warps_per_cta;
-    if (wpc <= 0) {
-        const long want = 4L * num_sms();
-        wpc = 8;
-        while (wpc > 1 && ((long)N * M * ((Lq + wpc - 1) / wpc) < want || wpc / 2 >= Lq)) wpc >>= 1;
+    const int LP = L * P;
+    const int stage_elems = ((3 * LP * (int)sizeof(T) + 15) / 16) * 16 / (int)sizeof(T);
+    const size_t smem = (size_t)L * sizeof(int4) +
+                        (size_t)kWarpsPerCta * (16 + 2 * (size_t)stage_elems * sizeof(T) + kTapsPerWarp * sizeof(Tap));
+    if (smem > 200 * 1024) { set_error("msda: L*P = %d too large for the staging buffers", LP); return MMFS_EUNSUPPORTED; }
+    auto kern = msda_fwd_rows_kernel<T, D>;
+    static thread_local size_t smem_set = 0;  // per (T, D) instantiation
+    if (smem > 48 * 1024 && smem > smem_set) {
+        MMFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
     }
-    const int mapping = g_mapping & 1;
-    const int qtiles = (Lq + wpc - 1) / wpc;
-    const long nrows = (long)N * Lq * M;
-    const long nb = mapping == 0 ? (long)N * M * qtiles : (nrows + wpc - 1) / wpc;
-    if (nb > 0x7fffffffL) { set_error("msda: grid too large (%ld CTAs)", nb); return MMFS_EUNSUPPORTED; }
-    const size_t smem = (size_t)L * sizeof(int4) + (X ? (size_t)wpc * 64 * sizeof(Tap) : 0);
-    if (smem > 48 * 1024) { set_error("msda: too many levels (%d)", L); return MMFS_EUNSUPPORTED; }
-    msda_fwd_warp_kernel<T, D, X><<<dim3((unsigned)nb), dim3(32 * wpc), smem, st>>>(
+    int ctas_per_sm = 0;
+    MMFS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 32 * kWarpsPerCta, smem));
+    if (ctas_per_sm < 1) { set_error("msda: kernel does not fit on an SM (smem %zu)", smem); return MMFS_EUNSUPPORTED; }
+    const int nsm = num_sms();
+    // rows per warp per tile: long enough to amortise staging and keep a CTA on one head, short
+    // enough that every SM gets work; tiny problems (decode, Lq = 1) use 1.
+    int rpw = g_rows_per_warp;
+    if (rpw <= 0) {
+        rpw = 8;
+        while (rpw > 1 && (long)N * M * ((Lq + kWarpsPerCta * rpw - 1) / (kWarpsPerCta * rpw)) < 2L * nsm * ctas_per_sm) rpw >>= 1;
+    }
+    const int qtiles = (Lq + kWarpsPerCta * rpw - 1) / (kWarpsPerCta * rpw);
+    const long ntiles = (long)N * M * qtiles;
+    if (ntiles > 0x3fffffffL) { set_error("msda: too many tiles (%ld)", ntiles); return MMFS_EUNSUPPORTED; }
+    const long full = (long)nsm * ctas_per_sm;
+    const unsigned grid = (unsigned)(ntiles < full ? ntiles : full);
+    const bool bulk_ok = ((uintptr_t)loc % 16 == 0) && ((uintptr_t)attn % 16 == 0) &&
+                         ((2 * LP * sizeof(T)) % 16 == 0) && ((LP * sizeof(T)) % 16 == 0);
+    kern<<<grid, 32 * kWarpsPerCta, smem, st>>>(
         (const T *)value, shapes, starts, (const T *)loc, (const T *)attn, (T *)out,
-        nrows, S, M, L, Lq, P, p_shift, flags, qtiles, mapping);
+        S, M, L, Lq, P, p_shift, flags, rpw, qtiles, ntiles, ctas_per_sm, nsm, stage_elems,
+        bulk_ok ? 1 : 0, (g_mapping & 1) ? 0 : 1);
     MMFS_CUDA(cudaGetLastError());
     return MMFS_OK;
 }
@@ -386,14 +467,10 @@ template <typename T>
 static int dispatch_d(const void *value, const int64_t *shapes, const int64_t *starts, const void *loc,
                       const void *attn, void *out, int N, int S, int M, int D, int L, int Lq, int P,
                       unsigned flags, cudaStream_t st) {
-    const bool shfl = g_mapping & 2;
-#define MMFS_CASE(DD)                                                                                     \
-    case DD:                                                                                              \
-        return shfl ? launch_warp<T, DD, false>(value, shapes, starts, loc, attn, out, N, S, M, L, Lq, P, flags, st) \
-                    : launch_warp<T, DD, true>(value, shapes, starts, loc, attn, out, N, S, M, L, Lq, P, flags, st);
-    const bool aligned16 = ((uintptr_t)value % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
-                           ((uintptr_t)loc % 8 == 0) && ((uintptr_t)attn % 4 == 0);
-    if (aligned16 && (long)S * M * D * (long)sizeof(T) < (1L << 32)) {
+#define MMFS_CASE(DD) \
+    case DD: return launch_rows<T, DD>(value, shapes, starts, loc, attn, out, N, S, M, L, Lq, P, flags, st);
+    const bool aligned16 = ((uintptr_t)value % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    if (aligned16) {
         switch (D) {
             MMFS_CASE(32)
             MMFS_CASE(64)
@@ -409,12 +486,12 @@ static int dispatch_d(const void *value, const int64_t *shapes, const int64_t *s
 
 using namespace mmfs;
 
-extern "C" int mmfs_msda_set_tuning(int warps_per_cta, int mapping) {
-    if (warps_per_cta < 0 || warps_per_cta > 8 || (warps_per_cta & (warps_per_cta - 1))) {
-        set_error("mmfs_msda_set_tuning: warps_per_cta must be 0 or a power of two <= 8");
+extern "C" int mmfs_msda_set_tuning(int rows_per_warp, int mapping) {
+    if (rows_per_warp < 0 || rows_per_warp > 64) {
+        set_error("mmfs_msda_set_tuning: rows_per_warp must be in [0, 64]");
         return MMFS_EINVAL;
     }
-    g_warps_per_cta = warps_per_cta;
+    g_rows_per_warp = rows_per_warp;
     g_mapping = mapping;
     return MMFS_OK;
 }

@@ -40,7 +40,7 @@ def test_argument_validation_without_gpu():
     # empty batch is a no-op success (the reference returns an empty tensor)
     rc = lib.mmfs_msda_forward(None, None, None, None, None, None, 0, 4, 1, 8, 1, 1, 1, _lib.F32, 0, None)
     assert rc == _lib.OK
-    assert lib.mmfs_msda_set_tuning(3, 0) == _lib.EINVAL
+    assert lib.mmfs_msda_set_tuning(-1, 0) == _lib.EINVAL
     assert lib.mmfs_msda_set_tuning(0, 0) == _lib.OK
 
 
