@@ -95,8 +95,47 @@ int mmfs_msda_forward_host(const void *value, const int64_t *spatial_shapes, con
                            int dtype, unsigned flags, void *stream);
 void mmfs_release_scratch(void);
 
-/* Tuning knobs (benchmarks / tests only): warps per CTA (0 = automatic). */
-int mmfs_msda_set_tuning(int warps_per_cta, int mapping);
+/* Tuning knobs (benchmarks / tests only): rows per warp per tile (0 = automatic); mapping bit 0 =
+ * plain tile order instead of the per-SM swizzle. */
+int mmfs_msda_set_tuning(int rows_per_warp, int mapping);
+
+/*
+ * Fused MMFS sampler: relpos-conditioned offsets / logits, image mask, null-slot softmax, sampling
+ * locations and the deformable gather in one kernel.
+ * Replaces MMFS.forward's middle section, ops/modules/mmfs.py:178-273 (everything between the
+ * query projections and output_proj), including its MSDeformAttnFunction.apply call.
+ *
+ *   value        (N, S, M, D)  dtype; S = n_img * sum(H_l*W_l)               (mmfs.py:165-172)
+ *   shapes       (n_img*n_lvl, 2) int64 [H,W], device; starts (n_img*n_lvl,) int64, device
+ *   qproj        (N, Lq, C) dtype, C = M*P*2 + M*n_lvl*(P+1): [sampling_offsets | attention_weights]
+ *                applied to dynamic_offset_mask(query), biases included   (mmfs.py:175,181,188)
+ *   rtable       (R, C) dtype: the same two linears (no bias) applied to query_relpos.weight
+ *   relpos       (N, n_img, Lq_r) uint8, Lq_r in {1, Lq}: relative image index, 0 = masked
+ *                                                                            (mmfs.py:154-163)
+ *   refpts       (Nr, Lq, Lr, 2) fp32, Nr in {1,N}, Lr in {1, n_img*n_lvl}   (mmfs.py:243-250)
+ *   scale_ratios (n_lvl,) fp32                                                (mmfs.py:80-83)
+ *   out          (N, Lq, M*D) dtype: the sampled features (input of output_proj, before the
+ *                ignore-token term)
+ *   null_mass    (N, Lq, M) fp32 or NULL: sum over levels of the null-slot weights, the factor of
+ *                ignore_token in mmfs.py:236-241
+ */
+int mmfs_sampler_forward(const void *value, const int64_t *shapes, const int64_t *starts,
+                         const void *qproj, const void *rtable, const uint8_t *relpos,
+                         const float *refpts, const float *scale_ratios, void *out, float *null_mass,
+                         int N, int S, int M, int D, int n_img, int n_lvl, int Lq, int P,
+                         int Lq_r, int Nr, int Lr, int R, int dtype, unsigned flags, void *stream);
+
+/*
+ * Same front-end, but materialises what the reference materialises: sampling_locations
+ * (N,Lq,M,L,P,2) and attention_weights (N,Lq,M,L,P) in dtype (mmfs.py:226-234, 243-265), L =
+ * n_img*n_lvl.  Parity instrumentation, and the route for head sizes without a fused gather path
+ * (follow with mmfs_msda_forward).
+ */
+int mmfs_sampler_locw(const int64_t *shapes, const int64_t *starts, const void *qproj, const void *rtable,
+                      const uint8_t *relpos, const float *refpts, const float *scale_ratios,
+                      void *loc_out, void *attn_out, float *null_mass,
+                      int N, int M, int n_img, int n_lvl, int Lq, int P,
+                      int Lq_r, int Nr, int Lr, int R, int dtype, void *stream);
 
 #ifdef __cplusplus
 }

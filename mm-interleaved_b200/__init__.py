@@ -12,5 +12,7 @@ from .msda import (  # noqa: F401
     msda_index_stream,
 )
 from .functions import MSDeformAttnFunction  # noqa: F401
+from .sampler import mmfs_sampler_forward, mmfs_sampler_locw  # noqa: F401
+from .mmfs import MMFS  # noqa: F401
 
 __version__ = "0.1.0"

@@ -28,6 +28,8 @@ SIGNATURES = {
     "mmfs_msda_forward_host": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _U, _P]),
     "mmfs_release_scratch": (None, []),
     "mmfs_msda_set_tuning": (_I, [_I, _I]),
+    "mmfs_sampler_forward": (_I, [_P] * 10 + [_I] * 13 + [_U, _P]),
+    "mmfs_sampler_locw": (_I, [_P] * 10 + [_I] * 11 + [_P]),
 }
 
 

@@ -23,116 +23,9 @@
 // The sampling-point index math (point_geom) is the single statement shared by the
 // forward kernels and by the index-stream kernel that the parity tests compare
 // bit-for-bit with oracle/msda_ref.c.
-#include "common.cuh"
+#include "sampler_common.cuh"
 
 namespace mmfs {
-
-// ------------------------------------------------------------------------------------
-// Index math of one sampling point: cuh:287-291 (pixel coordinates, in-range predicate)
-// and cuh:41-48 (floor, lerp fractions).
-// ------------------------------------------------------------------------------------
-template <typename OP> struct PointGeom {
-    bool in_range;
-    int h_low, w_low;
-    OP lh, lw;
-};
-
-__device__ __forceinline__ PointGeom<float> point_geom(float x, float y, int H, int W) {
-    // cuh:287-288  `loc_h * spatial_h - 0.5`: the product is an opmath (float) multiply
-    // rounded on its own; the double literal then forces a separate subtraction (exact
-    // in double, rounded once to float) -- equivalent to an un-fused float subtract.
-    // __fmul_rn/__fsub_rn are never contracted into an FMA by nvcc.
-    const float h_im = __fsub_rn(__fmul_rn(y, (float)H), 0.5f);
-    const float w_im = __fsub_rn(__fmul_rn(x, (float)W), 0.5f);
-    PointGeom<float> g;
-    g.in_range = (h_im > -1.f) && (w_im > -1.f) && (h_im < (float)H) && (w_im < (float)W);  // cuh:291
-    const float hf = floorf(h_im), wf = floorf(w_im);                                       // cuh:41-42
-    g.h_low = (int)hf;
-    g.w_low = (int)wf;
-    g.lh = h_im - hf;  // cuh:46 (h - h_low; hf is integral, the subtraction is exact)
-    g.lw = w_im - wf;
-    return g;
-}
-
-__device__ __forceinline__ PointGeom<double> point_geom(double x, double y, int H, int W) {
-    // double dispatch (cu:65): same source expression as the reference, so nvcc applies the
-    // same contraction it applies there.
-    const double h_im = y * H - 0.5;
-    const double w_im = x * W - 0.5;
-    PointGeom<double> g;
-    g.in_range = (h_im > -1) && (w_im > -1) && (h_im < H) && (w_im < W);
-    const double hf = floor(h_im), wf = floor(w_im);
-    g.h_low = (int)hf;
-    g.w_low = (int)wf;
-    g.lh = h_im - hf;
-    g.lw = w_im - wf;
-    return g;
-}
-
-// corner k = 0..3 <-> reference v1..v4: (h_low,w_low) (h_low,w_high) (h_high,w_low) (h_high,w_high)
-// validity predicates exactly as cuh:59,65,71,77.
-__device__ __forceinline__ bool corner_valid(int corner, int h_low, int w_low, int H, int W) {
-    const bool okh = (corner & 2) ? (h_low + 1 <= H - 1) : (h_low >= 0);
-    const bool okw = (corner & 1) ? (w_low + 1 <= W - 1) : (w_low >= 0);
-    return okh && okw;
-}
-
-// ------------------------------------------------------------------------------------
-// Fast path: persistent CTAs, one warp per output row (b, q, m) at a time;
-// D * sizeof(T) in {64,128,256,512} bytes.
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ void fma2(float &a0, float &a1, float w0, float w1, float v0, float v1) {
-    // Blackwell packed fp32 FMA (fma.rn.f32x2): two accumulator updates per issue slot.
-    unsigned long long acc, vv, ww;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(acc) : "f"(a0), "f"(a1));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(vv) : "f"(v0), "f"(v1));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(ww) : "f"(w0), "f"(w1));
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(ww), "l"(vv));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(acc));
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// mbarrier + bulk async copy (TMA engine, SASS UBLKCP): one instruction stages a whole
-// sampling-location / attention-weight row of the next output row into shared memory.
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-                 "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-// 512 bytes of zeros: taps that must not contribute (outside the map, invalid corner, masked
-// image) are pointed here with weight 0, so the gather loop needs no predicates and a
-// non-finite `value` entry can never leak through a 0 * inf product.
-__device__ uint4 g_zero_row[32];
-
-struct __align__(16) Tap {  // mailbox record handed from the index-math lane to the fetching slot
-    long long off;          // byte offset from the head slab origin (or to g_zero_row)
-    float w0, w1;           // lerp weight * attention weight, duplicated for fma.rn.f32x2
-};
-
-template <typename T> __device__ __forceinline__ float elem_to_f32(const T *p);
-template <> __device__ __forceinline__ float elem_to_f32<float>(const float *p) { return *p; }
-template <> __device__ __forceinline__ float elem_to_f32<__half>(const __half *p) { return __half2float(*p); }
-template <> __device__ __forceinline__ float elem_to_f32<__nv_bfloat16>(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
-
-constexpr int kTapStride = 33;                      // 16-byte units between corner planes (bank skew)
-constexpr int kTapsPerWarp = 4 * kTapStride;        // mailbox entries per warp (32 points x 4 corners)
-constexpr int kWarpsPerCta = 8;
 
 // Shared-memory layout of one CTA (all offsets 16-byte aligned):
 //   int4     lvl[L]                              {H, W, level_start, -}
@@ -149,7 +42,6 @@ msda_fwd_rows_kernel(const T *__restrict__ value, const int64_t *__restrict__ sh
                      int stage_elems, int bulk_ok, int swizzle) {
     constexpr int VEC = 16 / (int)sizeof(T);  // channels per lane
     constexpr int LPR = D / VEC;              // lanes per value row
-    constexpr int RPI = 32 / LPR;             // rows (taps) fetched per warp instruction
     static_assert(D % VEC == 0 && LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "unsupported D");
 
     extern __shared__ int4 s_dyn[];
@@ -176,60 +68,34 @@ msda_fwd_rows_kernel(const T *__restrict__ value, const int64_t *__restrict__ sh
     const int slot = lane / LPR;
     const uint32_t loc_bytes = (uint32_t)(2 * LP * (int)sizeof(T)), att_bytes = (uint32_t)(LP * (int)sizeof(T));
 
-    // Work order.  A tile = kWarpsPerCta * rows_per_warp consecutive queries of ONE (b, m); tiles are
-    // numbered (b, m, q-tile) with the q-tile fastest.  CTA i of the persistent grid sits on SM
-    // (i % nsm) in the first (only) wave, so giving CTA i the tiles ((i % nsm) * ctas_per_sm +
-    // i / nsm) + k * grid makes all CTAs resident on one SM walk neighbouring q-tiles of the
-    // same head: the head's value slab stays L1-resident.
-    const long grid = gridDim.x;
-    long tile0 = blockIdx.x;
-    if (swizzle && grid == (long)nsm * ctas_per_sm) tile0 = (long)(blockIdx.x % nsm) * ctas_per_sm + blockIdx.x / nsm;
+    RowWalk walk;
+    walk.itiles = (int)ntiles; walk.igrid = (int)gridDim.x; walk.qtiles = qtiles; walk.M = M; walk.Lq = Lq;
+    walk.rows_per_warp = rows_per_warp; walk.warp = warp;
 
-    // Row sequence of this warp: rows r = 0..rows_per_warp-1 of tile, then tile += grid.  Rows past Lq
-    // (last q-tile) are skipped.  All 32-bit (host guarantees ntiles < 2^31).
-    struct Cursor { int tile, r, b, m, q; bool ok; };
-    const int itiles = (int)ntiles, igrid = (int)grid;
-    auto settle = [&](Cursor &c) {   // decode (tile, r) -> (b, m, q), skipping rows past Lq
-        for (;;) {
-            if (c.tile >= itiles) { c.ok = false; return; }
-            const int qt = c.tile % qtiles, bm = c.tile / qtiles;
-            c.m = bm % M; c.b = bm / M;
-            c.q = (qt * kWarpsPerCta + warp) * rows_per_warp + c.r;
-            if (c.q < Lq) { c.ok = true; return; }
-            c.r = 0; c.tile += igrid;  // the rest of this tile's rows are past Lq as well
-        }
-    };
-    auto advance = [&](Cursor c) -> Cursor {
-        if (++c.r == rows_per_warp) { c.r = 0; c.tile += igrid; }
-        settle(c);
-        return c;
-    };
     auto stage_row = [&](int b, int m, int q, int buf) {  // whole warp calls; fills stage[buf]
         const size_t qm = ((size_t)b * Lq + q) * M + m;
         T *dst = stage + buf * stage_elems;
         const T *lsrc = loc + qm * (size_t)LP * 2;
         const T *asrc = attn + qm * (size_t)LP;
-        if (bulk_ok) {
+        if (bulk_ok) {   // bulk async copies (TMA engine): two instructions stage the whole row
             if (lane == 0) {
                 mbar_expect_tx(&bar[buf], loc_bytes + att_bytes);
                 bulk_g2s(dst, lsrc, loc_bytes, &bar[buf]);
                 bulk_g2s(dst + 2 * LP, asrc, att_bytes, &bar[buf]);
             }
-        } else {  // rows not 16-byte aligned / sized: plain loads
+        } else {         // rows not 16-byte aligned / sized: plain loads
             for (int i = lane; i < 2 * LP; i += 32) dst[i] = lsrc[i];
             for (int i = lane; i < LP; i += 32) dst[2 * LP + i] = asrc[i];
         }
     };
 
-    Cursor cur;
-    cur.tile = (int)tile0; cur.r = 0; cur.b = cur.m = cur.q = 0; cur.ok = false;
-    settle(cur);
+    RowCursor cur = walk.first(ctas_per_sm, nsm, swizzle);
     unsigned n_staged = 0;  // rows staged so far: buffer = n & 1, parity = (n >> 1) & 1
     if (cur.ok) stage_row(cur.b, cur.m, cur.q, 0);
 
     while (cur.ok) {
         // look ahead: next valid row of this warp, staged into the other buffer right away
-        const Cursor nxt = advance(cur);
+        const RowCursor nxt = walk.next(cur);
         const int b = cur.b, m = cur.m, q = cur.q;
         const int buf = n_staged & 1;
         const unsigned parity = (n_staged >> 1) & 1;
@@ -250,77 +116,31 @@ msda_fwd_rows_kernel(const T *__restrict__ value, const int64_t *__restrict__ sh
         for (int p0 = 0; p0 < LP; p0 += 32) {
             // ---- phase 1: one sampling point per lane, four taps each ----------------------
             const int j = p0 + lane;
-            Tap t4[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { t4[k].off = zero_off; t4[k].w0 = 0.f; t4[k].w1 = 0.f; }
             bool live = false;
+            PointGeom<float> g;
+            g.in_range = false; g.h_low = g.w_low = 0; g.lh = g.lw = 0.f;
+            float a = 0.f;
+            int4 lv = make_int4(1, 1, 0, 0);
             if (j < LP) {
-                const float x = elem_to_f32(s_loc + 2 * j), y = elem_to_f32(s_loc + 2 * j + 1);
-                const float a = elem_to_f32(s_att + j);
-                const int l = (p_shift >= 0) ? (j >> p_shift) : (j / P);
-                const int4 lv = s_lvl[l];
-                const PointGeom<float> g = point_geom(x, y, lv.x, lv.y);
-                live = g.in_range && (strict || a != 0.f);
-                if (live) {
-                    const float hh = 1.f - g.lh, hw = 1.f - g.lw;                       // cuh:48
-                    const long long o00 = (long long)(lv.z + g.h_low * lv.y + g.w_low) * row_bytes;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (corner_valid(k, g.h_low, g.w_low, lv.x, lv.y)) {
-                            t4[k].off = o00 + ((k & 2) ? (long long)lv.y * row_bytes : 0ll) + ((k & 1) ? row_bytes : 0ll);
-                            const float wk = ((k & 2) ? g.lh : hh) * ((k & 1) ? g.lw : hw) * a;  // cuh:83
-                            t4[k].w0 = wk; t4[k].w1 = wk;
-                        }
-                    }
+                a = elem_to_f32(s_att + j);
+                if (strict || a != 0.f) {   // masked images: weight exactly 0 -> no geometry, no fetch
+                    const float x = elem_to_f32(s_loc + 2 * j), y = elem_to_f32(s_loc + 2 * j + 1);
+                    lv = s_lvl[(p_shift >= 0) ? (j >> p_shift) : (j / P)];
+                    g = point_geom(x, y, lv.x, lv.y);
+                    live = g.in_range;
                 }
             }
             const unsigned livemask = __ballot_sync(0xffffffffu, live);
             if (livemask == 0u) continue;  // e.g. 32 points of masked images: nothing to fetch
             __syncwarp();                  // previous pass finished reading the mailbox
-#pragma unroll
-            for (int k = 0; k < 4; ++k)    // corner planes skewed by one entry: conflict-free both ways
-                *reinterpret_cast<uint4 *>(&taps[k * kTapStride + lane]) = *reinterpret_cast<const uint4 *>(&t4[k]);
+            emit_taps(taps, lane, live, g, a, lv.x, lv.y, lv.z, row_bytes, zero_off);
             __syncwarp();
-
-            // ---- phase 2: slot s fetches tap (it*RPI + s) = (point, corner); 16 B per lane --
-            constexpr int NIT = 128 / RPI;                 // fetch instructions per pass
-            constexpr int G = NIT < 8 ? NIT : 8;           // fetches in flight per lane
-            constexpr int PPG = (G * RPI) / 4;             // points covered by one group
-#pragma unroll 1
-            for (int g0 = 0; g0 < NIT; g0 += G) {
-                const unsigned pm = (PPG >= 32) ? livemask : ((livemask >> ((g0 * RPI) / 4)) & ((1u << PPG) - 1u));
-                if (pm == 0u) continue;                    // warp-uniform: these points are all dead
-                Tap t[G];
-                uint4 v[G];
-#pragma unroll
-                for (int it = 0; it < G; ++it) {
-                    const int tix = (g0 + it) * RPI + slot;        // tap index = point * 4 + corner
-                    *reinterpret_cast<uint4 *>(&t[it]) =
-                        *reinterpret_cast<const uint4 *>(&taps[(tix & 3) * kTapStride + (tix >> 2)]);
-                }
-#pragma unroll
-                for (int it = 0; it < G; ++it) v[it] = ldg_nc_v4(vbase + t[it].off);
-#pragma unroll
-                for (int it = 0; it < G; ++it) {
-                    float f[VEC];
-                    Vec16<T>::unpack(v[it], f);
-#pragma unroll
-                    for (int k = 0; k < VEC; k += 2) fma2(acc[k], acc[k + 1], t[it].w0, t[it].w1, f[k], f[k + 1]);
-                }
-            }
+            // ---- phase 2 -------------------------------------------------------------------
+            gather_pass<T, D>(taps, livemask, vbase, slot, acc);
         }
 
-        // ---- epilogue: sum the RPI slots, one rounding, 16-byte stores ---------------------
-#pragma unroll
-        for (int off = LPR; off < 32; off <<= 1)
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
-        if (lane < LPR) {
-            const size_t qm = ((size_t)b * Lq + q) * M + m;
-            stg_v4(out + qm * D + lane * VEC, Vec16<T>::pack(acc));
-        }
+        store_row<T, D>(acc, out + (((size_t)b * Lq + q) * M + m) * D, lane);
         __syncwarp();  // all lanes done with stage[buf] before it is refilled two rows later
-
         cur = nxt;
     }
 }

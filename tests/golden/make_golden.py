@@ -65,6 +65,96 @@ def main():
         print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB  out {tuple(out32.shape)}")
 
 
+# ---------------------------------------------------------------------------------------------
+# MMFS module (ops/modules/mmfs.py:120-276) executed with the reference's own PyTorch core
+# ---------------------------------------------------------------------------------------------
+# name -> dict(ctor kwargs, N, Lq, n_img, mask kind, ref kind)
+MMFS_CASES = {
+    # LLM flavour: reference point (0.5,0.5), per-token 3-D mask with causal image visibility
+    "llm_tiny": dict(ctor=dict(d_model=192, d_query=192, d_value=128, d_out=192, n_levels=3, n_heads=2, n_points=8,
+                               ratio=128 / 192, spatial_shapes=[8, 4, 2], base_spatial_shape=4),
+                     N=2, Lq=19, n_img=3, mask="3d", ref="center", seed=0),
+    # decode step: Lq = 1 while the mask still has the prefill length -> last row is used (mmfs.py:161-162)
+    "llm_decode": dict(ctor=dict(d_model=192, d_query=192, d_value=128, d_out=192, n_levels=3, n_heads=2, n_points=8,
+                                 ratio=128 / 192, spatial_shapes=[8, 4, 2], base_spatial_shape=4),
+                       N=2, Lq=1, n_img=3, mask="3d_long", ref="center", seed=1),
+    # SD flavour: pixel-centre reference grid, 2-D mask, 4 levels, 1 conditioning image, D = 32
+    "sd_tiny": dict(ctor=dict(d_model=128, d_query=96, d_value=128, d_out=96, n_levels=4, n_heads=4, n_points=8,
+                              ratio=1.0, spatial_shapes=[8, 4, 2, 1], base_spatial_shape=4),
+                    N=2, Lq=16, n_img=1, mask="2d", ref="grid", seed=2),
+    # 2-D mask with a fully masked sample and an odd head size (generic sampler path), 2 images
+    "masked_2d": dict(ctor=dict(d_model=96, d_query=80, d_value=48, d_out=80, n_levels=2, n_heads=4, n_points=3,
+                                ratio=1.0, spatial_shapes=[6, 3], base_spatial_shape=3),
+                      N=3, Lq=7, n_img=2, mask="2d_masked", ref="center", seed=3),
+}
+
+
+def mmfs_case_inputs(case):
+    c = case["ctor"]
+    g = torch.Generator().manual_seed(1000 + case["seed"])
+    N, Lq, n_img = case["N"], case["Lq"], case["n_img"]
+    hw = sum(s * s for s in c["spatial_shapes"])
+    query = torch.randn((N, Lq, c["d_query"]), generator=g)
+    feat = torch.randn((N, n_img, hw, c["d_value"]), generator=g)
+    ss = torch.tensor([(s, s) for s in c["spatial_shapes"]] * n_img, dtype=torch.long)
+    starts = torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1]))
+    if case["mask"] == "3d":
+        mask = (torch.rand((N, Lq, n_img), generator=g) < 0.6).float()
+        mask[0, 0] = 0                                   # a token that sees no image at all
+        mask[1, -1] = 1
+    elif case["mask"] == "3d_long":
+        mask = (torch.rand((N, 11, n_img), generator=g) < 0.6).float()
+        mask[0, -1] = torch.tensor([1.0, 0.0, 1.0])
+    elif case["mask"] == "2d":
+        mask = torch.ones((N, n_img))
+    else:
+        mask = torch.tensor([[1.0, 1.0], [0.0, 0.0], [0.0, 1.0]])
+    if case["ref"] == "center":
+        ref = torch.full((1, Lq, 1, 2), 0.5)
+    else:
+        side = int(Lq ** 0.5)
+        ys, xs = torch.meshgrid(torch.arange(side), torch.arange(side), indexing="ij")
+        ref = torch.stack([(xs.flatten() + 0.5) / side, (ys.flatten() + 0.5) / side], -1)[None, :, None, :].float()
+    return query, ref, feat, ss, starts, mask
+
+
+def mmfs_case_module(ref_ns, case):
+    torch.manual_seed(2000 + case["seed"])
+    mod = ref_ns.mmfs.MMFS(**case["ctor"])
+    with torch.no_grad():                                 # make every branch observable
+        torch.nn.init.normal_(mod.sampling_offsets.weight, std=0.02)
+        torch.nn.init.normal_(mod.attention_weights.weight, std=0.05)
+        torch.nn.init.normal_(mod.attention_weights.bias, std=0.5)
+        torch.nn.init.normal_(mod.dynamic_offset_mask.weight, std=0.05)
+        torch.nn.init.normal_(mod.dynamic_offset_mask.bias, std=0.1)
+        torch.nn.init.normal_(mod.value_proj.bias, std=0.1)
+        torch.nn.init.normal_(mod.output_proj.bias, std=0.1)
+        mod.ignore_token.normal_(std=0.3)
+    return mod.eval()
+
+
+def make_mmfs(ref_ns):
+    for name, case in MMFS_CASES.items():
+        mod = mmfs_case_module(ref_ns, case)
+        query, ref, feat, ss, starts, mask = mmfs_case_inputs(case)
+        with torch.no_grad():
+            out32 = mod(query, ref, feat, ss, starts, None, mask)
+            mod64 = mod.double()
+            out64 = mod64(query.double(), ref.double(), feat.double(), ss, starts, None, mask.double())
+            mod.float()
+        arrays = {f"param/{k}": v.float().numpy() for k, v in mod.state_dict().items()}
+        arrays.update(query=query.numpy(), reference_points=ref.numpy(), input_flatten=feat.numpy(),
+                      spatial_shapes=ss.numpy(), level_start_index=starts.numpy(), attention_mask=mask.numpy(),
+                      out_fp32=out32.numpy(), out_fp64=out64.numpy())
+        path = os.path.join(HERE, f"mmfs_{name}.npz")
+        np.savez_compressed(path, **arrays)
+        print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB  out {tuple(out32.shape)}")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    main()
+    which = sys.argv[1:] or ["msda", "mmfs"]
+    if "msda" in which:
+        main()
+    if "mmfs" in which:
+        make_mmfs(ref_loader.load())
