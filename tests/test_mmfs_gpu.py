@@ -2,8 +2,8 @@
 the reference module (tests/golden/mmfs_*.npz) and against the CPU oracle's intermediates.
 
 Tolerances:
-  * fp32 module output vs the reference's fp64 run: max-rel <= 1e-3 (north-star tolerance), in
-    practice ~1e-5 (TF32 is NOT used: the tests pin torch.backends.cuda.matmul.allow_tf32=False);
+  * fp32 module output vs the reference's fp64 run: |err| <= 1e-3 * |ref| + 1e-6 (north-star 1e-3 rel, with
+    an absolute floor for outputs that are themselves ~0), in practice max-abs ~2e-7 (TF32 is NOT used: the tests pin torch.backends.cuda.matmul.allow_tf32=False);
   * materialised sampling locations / attention weights (fp32) vs the oracle restatement:
     max-abs <= 2e-6;
   * bf16 module output vs the fp32 golden: max-abs <= 4e-2 * max|ref| -- bf16 storage of weights,
@@ -47,8 +47,10 @@ def run_module(mod, t, dtype=torch.float32):
 def test_module_fp32_matches_reference_golden(name):
     params, t, kw, case = load_mmfs_case(name)
     out = run_module(build_module(case, params), t)
-    m = error_metrics(out, t["out_fp64"])
-    assert m["max_rel"] <= 1e-3 and m["max_abs"] <= 2e-5, m
+    ref = t["out_fp64"]
+    err = (out.double().cpu() - ref).abs()
+    assert (err <= 1e-3 * ref.abs() + 1e-6).all(), error_metrics(out, ref)
+    assert error_metrics(out, ref)["max_abs"] <= 2e-5
 
 
 @pytest.mark.parametrize("name", NAMES)
