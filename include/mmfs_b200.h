@@ -137,6 +137,37 @@ int mmfs_sampler_locw(const int64_t *shapes, const int64_t *starts, const void *
                       int N, int M, int n_img, int n_lvl, int Lq, int P,
                       int Lq_r, int Nr, int Lr, int R, int dtype, void *stream);
 
+/*
+ * Row-wise / element-wise kernels of the Llama-MMFS decoder layer (csrc/llama_ops_sm100.cu).
+ *   mmfs_rmsnorm   replaces LlamaRMSNorm.forward            decoders/modeling_llama_mmfs.py:53-70
+ *   mmfs_layernorm nn.LayerNorm over the last dim (weight / bias may be NULL)
+ *   mmfs_rope_qk   replaces apply_rotary_pos_emb            decoders/modeling_llama_mmfs.py:158-172
+ *                  q, k are rotated IN PLACE in the (B, T, H, hd) layout of the projection output
+ *                  (row strides in elements); cos/sin tables are fp32 (max_pos, hd) as built by
+ *                  LlamaRotaryEmbedding (:119-151); position_ids int64 (B*T) or (T) when pos_per_batch=0
+ *   mmfs_swiglu    replaces act_fn(gate_proj(x)) * up_proj(x) decoders/modeling_llama_mmfs.py:188-189
+ *                  on one (rows, 2*inter) buffer holding [gate | up]
+ */
+int mmfs_rmsnorm(const void *x, const void *weight, void *y, long rows, int cols, float eps, int dtype, void *stream);
+int mmfs_layernorm(const void *x, const void *weight, const void *bias, void *y, long rows, int cols, float eps,
+                   int dtype, void *stream);
+int mmfs_rope_qk(void *q, void *k, const float *cos_table, const float *sin_table, const int64_t *position_ids,
+                 long n_tokens, int T_len, int H, int hd, int q_stride, int k_stride, int pos_per_batch,
+                 int dtype, void *stream);
+int mmfs_swiglu(const void *gate_up, void *out, long rows, int inter, int dtype, void *stream);
+
+/*
+ * softmax(q k^T * scale + mask) v for decode (q_len = 1 over a KV cache) and small / odd shapes;
+ * the tensor-core path for prefill shapes is mmfs_attn_forward.
+ * Replaces the eager attention of LlamaAttention.forward (decoders/modeling_llama_mmfs.py:246-264).
+ * q (B,Tq,H,hd), k/v (B,Tkv,H,hd), out (B,Tq,H,hd) with batch / token strides in elements;
+ * key_mask (B,Tkv) uint8 1 = attend, or NULL; causal: query i sees keys j <= past + i.
+ */
+int mmfs_attn_generic(const void *q, const void *k, const void *v, void *out, const uint8_t *key_mask,
+                      int B, int H, int Tq, int Tkv, int hd,
+                      long q_bs, long q_ts, long k_bs, long k_ts, long v_bs, long v_ts, long o_bs, long o_ts,
+                      float scale, int causal, int past, int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@ MSDA_STRICT = 1
 _lib = None
 
 _I, _U, _P = ctypes.c_int, ctypes.c_uint, ctypes.c_void_p
+_L, _F = ctypes.c_long, ctypes.c_float
 
 # name -> (restype, argtypes); every symbol include/mmfs_b200.h declares
 SIGNATURES = {
@@ -30,6 +31,11 @@ SIGNATURES = {
     "mmfs_msda_set_tuning": (_I, [_I, _I]),
     "mmfs_sampler_forward": (_I, [_P] * 10 + [_I] * 13 + [_U, _P]),
     "mmfs_sampler_locw": (_I, [_P] * 10 + [_I] * 11 + [_P]),
+    "mmfs_rmsnorm": (_I, [_P, _P, _P, _L, _I, _F, _I, _P]),
+    "mmfs_layernorm": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P]),
+    "mmfs_rope_qk": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "mmfs_swiglu": (_I, [_P, _P, _L, _I, _I, _P]),
+    "mmfs_attn_generic": (_I, [_P] * 5 + [_I] * 5 + [_L] * 8 + [_F, _I, _I, _I, _P]),
 }
 
 

@@ -1,0 +1,315 @@
+"""Llama decoder with injected MMFS cross-attention, B200-native.
+
+Mirrors the module / parameter naming and the forward signatures of the reference's
+``mm_interleaved/models/decoders/modeling_llama_mmfs.py`` (LlamaRMSNorm :53, LlamaMLP :175,
+LlamaAttention :192, LlamaMMFSAttention :311, LlamaDecoderLayer :370, LlamaModel :562) so that a
+reference checkpoint's state dict loads unchanged (``layers.N.self_attn.q_proj.weight`` ...), but
+the forward is built for B200:
+
+* q/k/v and gate/up projections run as ONE cuBLAS GEMM each on concatenated weights; o_proj and
+  down_proj fold the residual add into the GEMM (``addmm``, beta = 1);
+* RMSNorm, RoPE, SwiGLU and attention are hand-written sm_100a kernels (ops.py); q/k/v stay in the
+  GEMM's (B, T, H, hd) layout -- no transposes, no materialised (B, H, T, T) score tensor, no
+  additive 4-D mask (causality + key padding are applied inside the attention kernel);
+* the MMFS cross-attention uses the fused sampler (mmfs.py); RMSNorm(vision) and
+  value_proj(vision) are computed once per vision tensor and reused by every decode step
+  (the reference recomputes both at each of the 10 cross layers at every generated token,
+  SURVEY.md 3.2).
+
+Plain library GEMMs (cuBLAS via torch) are used for the dense linears.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from types import SimpleNamespace
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from .mmfs import MMFS
+
+
+@dataclass
+class LlamaMMFSConfig:
+    """The fields of HF ``LlamaConfig`` the reference reads, plus its three additions
+    (cross_attention_frequency, spatial_shapes, image_embed_dim; mm_interleaved.py:300-304)."""
+    vocab_size: int = 32002
+    hidden_size: int = 5120
+    intermediate_size: int = 13824
+    num_hidden_layers: int = 40
+    num_attention_heads: int = 40
+    hidden_act: str = "silu"
+    max_position_embeddings: int = 2048
+    rms_norm_eps: float = 1e-6
+    pad_token_id: int = 0
+    cross_attention_frequency: int = 4
+    spatial_shapes: List[int] = field(default_factory=lambda: [32, 16, 8])
+    image_embed_dim: int = 1024
+    use_cache: bool = True
+
+
+class LlamaRMSNorm(nn.Module):
+    def __init__(self, hidden_size, eps=1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+        self.variance_epsilon = eps
+
+    def forward(self, hidden_states):
+        return ops.rmsnorm(hidden_states.contiguous(), self.weight, self.variance_epsilon)
+
+
+def rotary_tables(dim: int, max_pos: int, base: float = 10000.0, device=None):
+    """cos / sin tables of FixedLlamaRotaryEmbedding (modeling_llama_mmfs.py:119-151), fp32 (max_pos, dim)."""
+    inv_freq = 1.0 / (base ** (torch.arange(0, dim, 2, device=device).float() / dim))
+    t = torch.arange(max_pos, device=device, dtype=torch.float32)
+    freqs = torch.outer(t, inv_freq)
+    emb = torch.cat((freqs, freqs), dim=-1)
+    return emb.cos().contiguous(), emb.sin().contiguous()
+
+
+class _CatWeight:
+    """Concatenation of several Linear weights along the output dim, rebuilt when a source changes."""
+
+    def __init__(self, *linears):
+        self.linears = linears
+        self.key = None
+        self.weight = None
+
+    def get(self):
+        key = tuple((l.weight.data_ptr(), l.weight._version, l.weight.dtype, l.weight.device) for l in self.linears)
+        if key != self.key:
+            with torch.no_grad():
+                self.weight = torch.cat([l.weight for l in self.linears], 0).contiguous()
+            self.key = key
+        return self.weight
+
+
+class LlamaMLP(nn.Module):
+    def __init__(self, hidden_size: int, intermediate_size: int, hidden_act: str):
+        super().__init__()
+        if hidden_act != "silu":
+            raise NotImplementedError("only the SiLU gate of Llama is implemented")
+        self.gate_proj = nn.Linear(hidden_size, intermediate_size, bias=False)
+        self.down_proj = nn.Linear(intermediate_size, hidden_size, bias=False)
+        self.up_proj = nn.Linear(hidden_size, intermediate_size, bias=False)
+        self._gate_up = _CatWeight(self.gate_proj, self.up_proj)
+
+    def forward(self, x, residual=None):
+        gu = F.linear(x, self._gate_up.get())                 # [gate | up] in one GEMM
+        act = ops.swiglu(gu)
+        if residual is None:
+            return self.down_proj(act)
+        out = torch.addmm(residual.reshape(-1, residual.shape[-1]), act.reshape(-1, act.shape[-1]), self.down_proj.weight.t())
+        return out.view_as(residual)
+
+
+class LlamaAttention(nn.Module):
+    def __init__(self, config: LlamaMMFSConfig):
+        super().__init__()
+        self.config = config
+        self.hidden_size = config.hidden_size
+        self.num_heads = config.num_attention_heads
+        self.head_dim = self.hidden_size // self.num_heads
+        self.max_position_embeddings = config.max_position_embeddings
+        if self.head_dim * self.num_heads != self.hidden_size:
+            raise ValueError("hidden_size must be divisible by num_heads")
+        self.q_proj = nn.Linear(self.hidden_size, self.hidden_size, bias=False)
+        self.k_proj = nn.Linear(self.hidden_size, self.hidden_size, bias=False)
+        self.v_proj = nn.Linear(self.hidden_size, self.hidden_size, bias=False)
+        self.o_proj = nn.Linear(self.hidden_size, self.hidden_size, bias=False)
+        self._qkv = _CatWeight(self.q_proj, self.k_proj, self.v_proj)
+        self._rope = None   # (device, max_pos, cos, sin)
+
+    def rope_tables(self, device, need_pos):
+        if self._rope is None or self._rope[0] != device or self._rope[1] < need_pos:
+            n = max(self.max_position_embeddings, need_pos)
+            self._rope = (device, n) + rotary_tables(self.head_dim, n, device=device)
+        return self._rope[2], self._rope[3]
+
+    def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,
+                output_attentions=False, use_cache=False, residual=None):
+        """``attention_mask``: (B, T_kv) key-padding mask, 1 = attend (what LlamaModel.forward receives,
+        modeling_llama_mmfs.py:625) or None.  Causality is implicit (decoder).  Returns
+        (attn_output [+ residual], None, present_key_value) like the reference (:217-280); the cache
+        holds (key, value) in (B, T, H, hd) layout."""
+        if output_attentions:
+            raise NotImplementedError("attention probabilities are never materialised by the fused kernel")
+        B, T, _ = hidden_states.shape
+        H, hd = self.num_heads, self.head_dim
+        qkv = F.linear(hidden_states, self._qkv.get()).view(B, T, 3, H, hd)
+        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+        past = 0 if past_key_value is None else past_key_value[0].shape[1]
+        if position_ids is None:
+            position_ids = torch.arange(past, past + T, device=hidden_states.device)
+        cos, sin = self.rope_tables(hidden_states.device, past + T)
+        ops.rope_qk_(q, k, cos, sin, position_ids)
+        if past_key_value is not None:
+            k = torch.cat([past_key_value[0], k], dim=1)
+            v = torch.cat([past_key_value[1], v], dim=1)
+        present = (k, v) if use_cache else None
+        key_mask = None
+        if attention_mask is not None:
+            if attention_mask.dim() == 4:   # reference-style additive (B,1,T,T_kv): keys visible to the last query
+                key_mask = attention_mask[:, 0, -1, :] > (torch.finfo(attention_mask.dtype).min / 2)
+            else:
+                key_mask = attention_mask
+        ctx = ops.attention(q, k, v, key_mask=key_mask, causal=True, past=past)       # (B, T, H*hd)
+        if residual is None:
+            out = self.o_proj(ctx)
+        else:
+            out = torch.addmm(residual.reshape(-1, self.hidden_size), ctx.view(-1, self.hidden_size),
+                              self.o_proj.weight.t()).view_as(residual)
+        return out, None, present
+
+
+class LlamaMMFSAttention(nn.Module):
+    def __init__(self, config: LlamaMMFSConfig, layer_idx):
+        super().__init__()
+        self.layer_idx = layer_idx
+        self.config = config
+        self.spatial_shapes = [(s, s) for s in config.spatial_shapes]
+        self.hidden_size = config.hidden_size
+        self.vision_hidden_size = config.image_embed_dim
+        self.gate = nn.Parameter(torch.tensor([0.0]))
+        self.attn = MMFS(layer_idx=layer_idx, d_model=self.hidden_size, d_query=self.hidden_size,
+                         d_value=self.vision_hidden_size, d_out=self.hidden_size,
+                         n_levels=len(config.spatial_shapes), n_heads=16, n_points=8,
+                         ratio=self.vision_hidden_size / self.hidden_size, offset_init_magnitude=3.0,
+                         spatial_shapes=config.spatial_shapes, max_num_image_per_seq=50)
+        self.norm1 = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.norm2 = LlamaRMSNorm(self.vision_hidden_size, eps=config.rms_norm_eps)
+        self._vision_cache = None   # (key, normalised vision features)
+        self._geom_cache = {}       # (device, n_img) -> (shapes, starts); (device, Lq) -> reference points
+
+    def _geometry(self, device, n_img, hw, len_q):
+        """deform_inputs (modeling_llama_mmfs.py:298-308) without its per-call host sync."""
+        per_img = sum(h * w for h, w in self.spatial_shapes)
+        if hw != per_img:
+            raise RuntimeError(f"vision features have {hw} positions per image, expected {per_img}")
+        key = ("s", device, n_img)
+        if key not in self._geom_cache:
+            ss = torch.tensor(self.spatial_shapes * n_img, dtype=torch.long)
+            starts = torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1]))
+            self._geom_cache[key] = (ss.to(device), starts.to(device))
+        rkey = ("r", device, len_q)
+        if rkey not in self._geom_cache:   # get_reference_points([(1,1)]): (0.5, 0.5) for every token (:306-307)
+            self._geom_cache[rkey] = torch.full((1, len_q, 1, 2), 0.5, dtype=torch.float32, device=device)
+        return self._geom_cache[key] + (self._geom_cache[rkey],)
+
+    def forward(self, hidden_states, vision_hidden_states=None, cross_attention_mask=None, residual=None):
+        h = self.norm1(hidden_states)
+        vkey = (vision_hidden_states.data_ptr(), tuple(vision_hidden_states.shape), vision_hidden_states._version,
+                self.norm2.weight._version)
+        if self._vision_cache is None or self._vision_cache[0] != vkey:
+            self._vision_cache = (vkey, self.norm2(vision_hidden_states))
+        v = self._vision_cache[1]
+        _, n_img, hw, _ = v.shape
+        shapes, starts, ref = self._geometry(h.device, n_img, hw, h.shape[1])
+        out = self.attn(query=h, reference_points=ref, input_flatten=v, input_spatial_shapes=shapes,
+                        input_level_start_index=starts, input_padding_mask=None, attention_mask=cross_attention_mask)
+        gate = self.gate.tanh().to(out.dtype)
+        if residual is None:
+            return out * gate
+        return torch.addcmul(residual, out, gate)
+
+
+class LlamaDecoderLayer(nn.Module):
+    def __init__(self, config: LlamaMMFSConfig, use_cross_attn: bool, layer_idx):
+        super().__init__()
+        self.hidden_size = config.hidden_size
+        self.self_attn = LlamaAttention(config=config)
+        self.layer_idx = layer_idx
+        self.llama_cross_attn = LlamaMMFSAttention(config=config, layer_idx=layer_idx) if use_cross_attn else None
+        self.mlp = LlamaMLP(self.hidden_size, config.intermediate_size, config.hidden_act)
+        self.input_layernorm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.post_attention_layernorm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+
+    def forward(self, hidden_states, vision_hidden_states, cross_attention_mask, attention_mask=None,
+                position_ids=None, past_key_value=None, output_attentions=False, use_cache=False):
+        # norm -> self-attn -> (+) -> [MMFS cross-attn -> (+)] -> norm -> SwiGLU -> (+)   (:418-441)
+        residual = hidden_states.contiguous()
+        h = self.input_layernorm(residual)
+        hidden_states, _, present = self.self_attn(h, attention_mask=attention_mask, position_ids=position_ids,
+                                                   past_key_value=past_key_value, use_cache=use_cache, residual=residual)
+        if self.llama_cross_attn is not None and vision_hidden_states is not None:
+            hidden_states = self.llama_cross_attn(hidden_states, vision_hidden_states, cross_attention_mask,
+                                                  residual=hidden_states)
+        h = self.post_attention_layernorm(hidden_states)
+        hidden_states = self.mlp(h, residual=hidden_states)
+        outputs = (hidden_states,)
+        if use_cache:
+            outputs += (present,)
+        return outputs
+
+
+class LlamaModel(nn.Module):
+    """Transformer decoder of ``config.num_hidden_layers`` layers with an MMFS cross-attention block in every
+    ``cross_attention_frequency``-th layer (modeling_llama_mmfs.py:562-752)."""
+
+    def __init__(self, config: LlamaMMFSConfig):
+        super().__init__()
+        self.config = config
+        self.padding_idx = config.pad_token_id
+        self.vocab_size = config.vocab_size
+        self.cross_attention_frequency = config.cross_attention_frequency
+        self.embed_tokens = nn.Embedding(config.vocab_size, config.hidden_size, self.padding_idx)
+        use_cross = [i % self.cross_attention_frequency == 0 for i in range(config.num_hidden_layers)]
+        self.layers = nn.ModuleList([LlamaDecoderLayer(config, use_cross[i], i) for i in range(config.num_hidden_layers)])
+        self.norm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.gradient_checkpointing = False
+
+    def get_input_embeddings(self):
+        return self.embed_tokens
+
+    def set_input_embeddings(self, value):
+        self.embed_tokens = value
+
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None,
+                inputs_embeds=None, vision_hidden_states=None, cross_attention_mask=None, use_cache=None,
+                output_attentions=None, output_hidden_states=None, return_dict=None):
+        use_cache = self.config.use_cache if use_cache is None else use_cache
+        return_dict = True if return_dict is None else return_dict
+        if output_attentions:
+            raise NotImplementedError("attention probabilities are never materialised")
+        if input_ids is not None and inputs_embeds is not None:
+            raise ValueError("You cannot specify both decoder_input_ids and decoder_inputs_embeds at the same time")
+        if input_ids is None and inputs_embeds is None:
+            raise ValueError("You have to specify either decoder_input_ids or decoder_inputs_embeds")
+        if inputs_embeds is None:
+            inputs_embeds = self.embed_tokens(input_ids)
+        B, T, _ = inputs_embeds.shape
+        past = 0 if past_key_values is None else past_key_values[0][0].shape[1]
+        if position_ids is None:
+            position_ids = torch.arange(past, past + T, dtype=torch.long, device=inputs_embeds.device)
+        else:
+            position_ids = position_ids.view(-1, T).long()
+        key_mask = None
+        if attention_mask is not None:
+            if tuple(attention_mask.shape) != (B, past + T):
+                raise ValueError(f"attention_mask should be of size {(B, past + T)}, but is {tuple(attention_mask.shape)}")
+            key_mask = attention_mask.to(torch.uint8)
+
+        hidden_states = inputs_embeds
+        all_hidden = () if output_hidden_states else None
+        next_cache = () if use_cache else None
+        for idx, layer in enumerate(self.layers):
+            if output_hidden_states:
+                all_hidden += (hidden_states,)
+            outs = layer(hidden_states, vision_hidden_states, cross_attention_mask, attention_mask=key_mask,
+                         position_ids=position_ids,
+                         past_key_value=past_key_values[idx] if past_key_values is not None else None,
+                         use_cache=use_cache)
+            hidden_states = outs[0]
+            if use_cache:
+                next_cache += (outs[1],)
+        hidden_states = self.norm(hidden_states)
+        if output_hidden_states:
+            all_hidden += (hidden_states,)
+        if not return_dict:
+            return tuple(v for v in [hidden_states, next_cache, all_hidden] if v is not None)
+        return SimpleNamespace(last_hidden_state=hidden_states, past_key_values=next_cache, hidden_states=all_hidden,
+                               attentions=None)

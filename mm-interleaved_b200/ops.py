@@ -1,0 +1,106 @@
+"""Tensor-level wrappers of the decoder-layer kernels (csrc/llama_ops_sm100.cu, csrc/attn_*.cu).
+
+Host side is PyTorch (allocation, streams); every function enqueues exactly one hand-written kernel
+through the C ABI and raises if the library rejects the arguments -- there is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .msda import _DTYPE_CODE, _require
+
+launch_counter = [0]   # kernels of ours launched through this module (bench.py's gpu_launches)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
+    """LlamaRMSNorm.forward (decoders/modeling_llama_mmfs.py:53-70) over the last dim."""
+    _require(x.is_cuda and x.is_contiguous() and weight.is_contiguous(), "rmsnorm: contiguous CUDA tensors required")
+    _require(weight.dtype == x.dtype and weight.numel() == x.shape[-1], "rmsnorm: weight dtype / size mismatch")
+    y = torch.empty_like(x)
+    rows = x.numel() // x.shape[-1]
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().mmfs_rmsnorm(x.data_ptr(), weight.data_ptr(), y.data_ptr(), rows, x.shape[-1], float(eps),
+                                     _DTYPE_CODE[x.dtype], _stream())
+    _lib.check(rc, "rmsnorm")
+    launch_counter[0] += 1
+    return y
+
+
+def layernorm(x: torch.Tensor, weight, bias, eps: float) -> torch.Tensor:
+    _require(x.is_cuda and x.is_contiguous(), "layernorm: contiguous CUDA tensor required")
+    y = torch.empty_like(x)
+    rows = x.numel() // x.shape[-1]
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().mmfs_layernorm(x.data_ptr(), weight.data_ptr() if weight is not None else None,
+                                       bias.data_ptr() if bias is not None else None, y.data_ptr(), rows, x.shape[-1],
+                                       float(eps), _DTYPE_CODE[x.dtype], _stream())
+    _lib.check(rc, "layernorm")
+    launch_counter[0] += 1
+    return y
+
+
+def rope_qk_(q: torch.Tensor, k: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, position_ids: torch.Tensor):
+    """In-place rotary embedding of q and k, both (B, T, H, hd) views whose last two dims are dense
+    (apply_rotary_pos_emb, decoders/modeling_llama_mmfs.py:165-172).  cos/sin: fp32 (max_pos, hd)."""
+    B, T, H, hd = q.shape
+    _require(q.is_cuda and k.shape == q.shape and q.stride(3) == 1 and q.stride(2) == hd and k.stride(3) == 1
+             and k.stride(2) == hd and q.stride(0) == T * q.stride(1) and k.stride(0) == T * k.stride(1),
+             "rope_qk_: q / k must be (B,T,H,hd) with dense heads and uniform token stride")
+    _require(cos.dtype == torch.float32 and sin.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous()
+             and cos.shape[-1] == hd, "rope_qk_: cos / sin must be contiguous fp32 (max_pos, hd)")
+    pos = position_ids.to(torch.int64).contiguous()
+    per_batch = 1 if pos.numel() == B * T else 0
+    _require(per_batch or pos.numel() == T, "rope_qk_: position_ids must have B*T or T entries")
+    with torch.cuda.device(q.device):
+        rc = _lib.lib().mmfs_rope_qk(q.data_ptr(), k.data_ptr(), cos.data_ptr(), sin.data_ptr(), pos.data_ptr(),
+                                     B * T, T, H, hd, q.stride(1), k.stride(1), per_batch, _DTYPE_CODE[q.dtype], _stream())
+    _lib.check(rc, "rope_qk_")
+    launch_counter[0] += 1
+
+
+def swiglu(gate_up: torch.Tensor) -> torch.Tensor:
+    """act_fn(gate) * up on a (..., 2*I) tensor holding [gate | up] (LlamaMLP, :188-189)."""
+    _require(gate_up.is_cuda and gate_up.is_contiguous() and gate_up.shape[-1] % 2 == 0, "swiglu: bad input")
+    inter = gate_up.shape[-1] // 2
+    out = torch.empty(gate_up.shape[:-1] + (inter,), dtype=gate_up.dtype, device=gate_up.device)
+    with torch.cuda.device(gate_up.device):
+        rc = _lib.lib().mmfs_swiglu(gate_up.data_ptr(), out.data_ptr(), gate_up.numel() // (2 * inter), inter,
+                                    _DTYPE_CODE[gate_up.dtype], _stream())
+    _lib.check(rc, "swiglu")
+    launch_counter[0] += 1
+    return out
+
+
+def attention(q, k, v, key_mask=None, causal=True, past=0, scale=None, force_generic=False) -> torch.Tensor:
+    """softmax(q k^T * scale + mask) v.  q (B,Tq,H,hd), k/v (B,Tkv,H,hd) -- any batch / token strides, heads
+    dense; key_mask (B,Tkv) bool/uint8 (1 = attend) or None; causal: query i sees keys j <= past + i.
+    Returns (B, Tq, H*hd).  Prefill shapes go to the tcgen05 kernel, decode / odd shapes to the
+    bandwidth kernel (see csrc/attn_generic_sm100.cu)."""
+    B, Tq, H, hd = q.shape
+    Tkv = k.shape[1]
+    for t in (q, k, v):
+        _require(t.is_cuda and t.stride(3) == 1 and t.stride(2) == hd, "attention: heads must be dense (.., H, hd)")
+    _require(k.shape == v.shape and k.shape[0] == B and k.shape[2] == H and k.shape[3] == hd, "attention: k/v shape mismatch")
+    scale = float(scale if scale is not None else hd ** -0.5)
+    out = torch.empty((B, Tq, H, hd), dtype=q.dtype, device=q.device)
+    km = None
+    if key_mask is not None:
+        km = key_mask.to(torch.uint8).contiguous()
+        _require(tuple(km.shape) == (B, Tkv), "attention: key_mask must be (B, Tkv)")
+    from . import attn_tc
+    if not force_generic and attn_tc.supported(q, k, v, Tq, Tkv, hd):
+        attn_tc.forward(q, k, v, out, km, causal, past, scale)
+    else:
+        with torch.cuda.device(q.device):
+            rc = _lib.lib().mmfs_attn_generic(
+                q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), km.data_ptr() if km is not None else None,
+                B, H, Tq, Tkv, hd, q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+                out.stride(0), out.stride(1), scale, 1 if causal else 0, int(past), _DTYPE_CODE[q.dtype], _stream())
+        _lib.check(rc, "attention")
+    launch_counter[0] += 1
+    return out.view(B, Tq, H * hd)

@@ -151,9 +151,94 @@ def make_mmfs(ref_ns):
         print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB  out {tuple(out32.shape)}")
 
 
+# ---------------------------------------------------------------------------------------------
+# Llama-MMFS decoder (decoders/modeling_llama_mmfs.py) -- tiny configuration, seeded weights
+# ---------------------------------------------------------------------------------------------
+LLAMA_TINY = dict(vocab_size=64, hidden_size=256, intermediate_size=512, num_hidden_layers=3, num_attention_heads=2,
+                  max_position_embeddings=64, rms_norm_eps=1e-6, pad_token_id=0, cross_attention_frequency=2,
+                  spatial_shapes=[8, 4, 2], image_embed_dim=512)
+
+
+def seeded_state_dict(template, seed):
+    """Deterministic weights for any module with the reference's parameter names: iterate the names in sorted
+    order with one CPU generator.  Used both here (loaded into the reference) and by the tests (loaded
+    into the B200 modules), so the multi-MB weights need not be stored in the fixtures."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for name in sorted(template.keys()):
+        t = template[name]
+        if not t.is_floating_point():
+            out[name] = t.clone()
+        elif name.endswith("norm.weight") or name.endswith("layernorm.weight") or ".norm1." in name or ".norm2." in name:
+            out[name] = 1.0 + 0.1 * torch.randn(t.shape, generator=g)
+        elif name.endswith(".gate"):
+            out[name] = torch.full(t.shape, 0.5)
+        elif name.endswith("sampling_offsets.bias"):
+            out[name] = torch.rand(t.shape, generator=g) * 6 - 3                  # U(-3,3), mmfs.py:103-110
+        elif name.endswith("ignore_token"):
+            out[name] = torch.zeros(t.shape)
+        elif name.endswith(".bias"):
+            out[name] = 0.1 * torch.randn(t.shape, generator=g)
+        elif name.endswith("embed_tokens.weight") or name.endswith("query_relpos.weight"):
+            out[name] = 0.5 * torch.randn(t.shape, generator=g)
+        else:
+            fan_in = t.shape[-1]
+            out[name] = torch.randn(t.shape, generator=g) / (fan_in ** 0.5)
+        if name.endswith("sampling_offsets.weight"):
+            out[name] = out[name] * 0.3
+    return out
+
+
+def llama_inputs(cfg, B, T, n_img, seed, left_pad=2):
+    g = torch.Generator().manual_seed(seed)
+    hw = sum(s * s for s in cfg["spatial_shapes"])
+    embeds = torch.randn((B, T, cfg["hidden_size"]), generator=g)
+    vision = torch.randn((B, n_img, hw, cfg["image_embed_dim"]), generator=g)
+    attn_mask = torch.ones((B, T), dtype=torch.long)
+    if left_pad and B > 1:
+        attn_mask[1, :left_pad] = 0                                    # eval batches are left-padded (collator.py:337)
+    position_ids = (attn_mask.cumsum(-1) - 1).clamp(min=0)             # causal_lm_cascade.py:179-185
+    cross = (torch.rand((B, T, n_img), generator=g) < 0.6).float()
+    cross[0, 0] = 0
+    return embeds, vision, attn_mask, position_ids, cross
+
+
+def make_llama(ref_ns):
+    from transformers import LlamaConfig
+    cfg = LlamaConfig(**{k: v for k, v in LLAMA_TINY.items() if k not in ("cross_attention_frequency", "spatial_shapes", "image_embed_dim")},
+                      hidden_act="silu")
+    cfg.cross_attention_frequency = LLAMA_TINY["cross_attention_frequency"]
+    cfg.spatial_shapes = LLAMA_TINY["spatial_shapes"]
+    cfg.image_embed_dim = LLAMA_TINY["image_embed_dim"]
+    model = ref_ns.llama.LlamaModel(cfg).eval()
+    sd = seeded_state_dict(model.state_dict(), seed=4242)
+    model.load_state_dict(sd)
+    B, T, n_img = 2, 12, 2
+    embeds, vision, attn_mask, position_ids, cross = llama_inputs(LLAMA_TINY, B, T, n_img, seed=99)
+    with torch.no_grad():
+        out = model(inputs_embeds=embeds, attention_mask=attn_mask, position_ids=position_ids,
+                    vision_hidden_states=vision, cross_attention_mask=cross, use_cache=True, return_dict=True)
+        # one decode step on top of the prefill cache (q_len = 1, mask / cross mask grown by one)
+        g = torch.Generator().manual_seed(7)
+        step = torch.randn((B, 1, LLAMA_TINY["hidden_size"]), generator=g)
+        attn2 = torch.cat([attn_mask, torch.ones((B, 1), dtype=torch.long)], 1)
+        pos2 = position_ids[:, -1:] + 1
+        cross2 = torch.cat([cross, cross[:, -1:]], 1)
+        out2 = model(inputs_embeds=step, attention_mask=attn2, position_ids=pos2, past_key_values=out.past_key_values,
+                     vision_hidden_states=vision, cross_attention_mask=cross2, use_cache=True, return_dict=True)
+        # (no fp64 run: the reference's _make_causal_mask overflows for float64, :28)
+    path = os.path.join(HERE, "llama_tiny.npz")
+    np.savez_compressed(path, prefill_fp32=out.last_hidden_state.numpy(),
+                        decode_fp32=out2.last_hidden_state.numpy(),
+                        weight_checksum=np.array(float(sum(v.double().sum() for v in sd.values()))))
+    print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["msda", "mmfs"]
+    which = sys.argv[1:] or ["msda", "mmfs", "llama"]
+    if "llama" in which:
+        make_llama(ref_loader.load())
     if "msda" in which:
         main()
     if "mmfs" in which:

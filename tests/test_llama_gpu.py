@@ -1,0 +1,140 @@
+"""GPU parity of the B200 Llama-MMFS decoder and its kernels.
+
+Tolerances: fp32 model output vs the reference's fp32 golden: |err| <= 1e-3*|ref| + 2e-5 at non-padding
+positions (north-star 1e-3 rel; fully masked = padding query rows are unspecified);
+kernels in fp32 vs a plain PyTorch fp32 statement of the same op: 1e-5 / 1e-4; bf16 kernels: one bf16 ulp.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import error_metrics  # noqa: E402
+from oracle.llama import additive_mask_ref, rotary_tables_ref  # noqa: E402
+from oracle.mmfs import rms_norm_ref  # noqa: E402
+from tests.golden.make_golden import LLAMA_TINY, llama_inputs  # noqa: E402
+from tests.test_oracle_llama import tiny_state_dict  # noqa: E402
+
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_rmsnorm_matches_reference_formula(dtype):
+    from mm_interleaved_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((3, 7, 5120), generator=g).to(dtype)
+    w = (1 + 0.1 * torch.randn(5120, generator=g)).to(dtype)
+    y = ops.rmsnorm(x.to(DEV), w.to(DEV), 1e-6).cpu()
+    ref = rms_norm_ref(x, w, 1e-6)
+    if dtype == torch.float32:
+        assert (y - ref).abs().max() < 1e-5
+    else:
+        assert ((y.float() - ref.float()).abs() <= ref.float().abs() * 2 ** -7 + 1e-6).all()
+        assert (y == ref).float().mean() > 0.98
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_rope_matches_reference_formula(dtype):
+    from mm_interleaved_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    B, T, H, hd = 2, 9, 3, 128
+    qkv = torch.randn((B, T, 3, H, hd), generator=g).to(dtype)
+    pos = torch.stack([torch.arange(T), (torch.arange(T) - 2).clamp(min=0)])
+    cos, sin = rotary_tables_ref(hd, 64)
+    d = qkv.to(DEV).clone()
+    ops.rope_qk_(d[:, :, 0], d[:, :, 1], cos.to(DEV), sin.to(DEV), pos.to(DEV))
+    c = cos.to(dtype)[pos][:, :, None]
+    s = sin.to(dtype)[pos][:, :, None]
+    rot = lambda x: torch.cat((-x[..., hd // 2:], x[..., : hd // 2]), -1)
+    for i in (0, 1):
+        ref = qkv[:, :, i] * c + rot(qkv[:, :, i]) * s
+        got = d[:, :, i].cpu()
+        if dtype == torch.float32:
+            assert (got - ref).abs().max() < 1e-6
+        else:
+            assert ((got.float() - ref.float()).abs() <= ref.float().abs() * 2 ** -7 + 1e-3).all()
+    assert torch.equal(d[:, :, 2].cpu(), qkv[:, :, 2])    # v untouched
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_swiglu_matches_reference_formula(dtype):
+    from mm_interleaved_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    gu = torch.randn((5, 3, 2 * 512), generator=g).to(dtype)
+    y = ops.swiglu(gu.to(DEV)).cpu()
+    ref = torch.nn.functional.silu(gu[..., :512]) * gu[..., 512:]
+    tol = 1e-6 if dtype == torch.float32 else 2 ** -7
+    assert ((y.float() - ref.float()).abs() <= ref.float().abs() * tol + 1e-6).all()
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 17, 17, 128, 0), (1, 2, 1, 40, 128, 39), (2, 4, 33, 33, 64, 0), (1, 2, 5, 300, 80, 295)])
+@pytest.mark.parametrize("causal", [True, False])
+def test_generic_attention_matches_eager(shape, causal):
+    from mm_interleaved_b200 import ops
+    B, H, Tq, Tkv, hd, past = shape
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn((B, Tq, H, hd), generator=g)
+    k = torch.randn((B, Tkv, H, hd), generator=g)
+    v = torch.randn((B, Tkv, H, hd), generator=g)
+    km = torch.ones((B, Tkv), dtype=torch.bool)
+    km[0, :3] = False
+    out = ops.attention(q.to(DEV), k.to(DEV), v.to(DEV), key_mask=km.to(DEV), causal=causal, past=past,
+                        force_generic=True).cpu().view(B, Tq, H, hd)
+    s = torch.einsum("bqhd,bkhd->bhqk", q * hd ** -0.5, k)
+    allow = km[:, None, None, :].expand(B, H, Tq, Tkv).clone()
+    if causal:
+        allow &= (torch.arange(Tkv)[None, :] <= past + torch.arange(Tq)[:, None])[None, None]
+    s = s.masked_fill(~allow, float("-inf"))
+    p = torch.softmax(s, -1).nan_to_num(0.0)
+    ref = torch.einsum("bhqk,bkhd->bqhd", p, v)
+    assert (out - ref).abs().max() < 2e-5
+
+
+def build_model(dtype):
+    model, sd, z = tiny_state_dict()
+    model.load_state_dict(sd, strict=True)
+    return model.to(DEV, dtype).eval(), z
+
+
+def test_model_fp32_prefill_and_decode_match_reference_golden():
+    model, z = build_model(torch.float32)
+    embeds, vision, attn_mask, position_ids, cross = llama_inputs(LLAMA_TINY, 2, 12, 2, seed=99)
+    with torch.no_grad():
+        out = model(inputs_embeds=embeds.to(DEV), attention_mask=attn_mask.to(DEV), position_ids=position_ids.to(DEV),
+                    vision_hidden_states=vision.to(DEV), cross_attention_mask=cross.to(DEV), use_cache=True)
+        ref = torch.from_numpy(z["prefill_fp32"])
+        valid = attn_mask.bool()
+        err = (out.last_hidden_state.cpu() - ref).abs()[valid]
+        assert (err <= 1e-3 * ref[valid].abs() + 2e-5).all(), err.max()
+        g = torch.Generator().manual_seed(7)
+        step = torch.randn((2, 1, LLAMA_TINY["hidden_size"]), generator=g)
+        attn2 = torch.cat([attn_mask, torch.ones((2, 1), dtype=torch.long)], 1)
+        cross2 = torch.cat([cross, cross[:, -1:]], 1)
+        out2 = model(inputs_embeds=step.to(DEV), attention_mask=attn2.to(DEV), position_ids=(position_ids[:, -1:] + 1).to(DEV),
+                     past_key_values=out.past_key_values, vision_hidden_states=vision.to(DEV),
+                     cross_attention_mask=cross2.to(DEV), use_cache=True)
+        ref2 = torch.from_numpy(z["decode_fp32"])
+        err2 = (out2.last_hidden_state.cpu() - ref2).abs()
+        assert (err2 <= 1e-3 * ref2.abs() + 2e-5).all(), err2.max()
+        assert out2.past_key_values[0][0].shape[1] == 13
+
+
+def test_model_bf16_tracks_fp32_reference():
+    model, z = build_model(torch.bfloat16)
+    embeds, vision, attn_mask, position_ids, cross = llama_inputs(LLAMA_TINY, 2, 12, 2, seed=99)
+    with torch.no_grad():
+        out = model(inputs_embeds=embeds.to(DEV, torch.bfloat16), attention_mask=attn_mask.to(DEV),
+                    position_ids=position_ids.to(DEV), vision_hidden_states=vision.to(DEV, torch.bfloat16),
+                    cross_attention_mask=cross.to(DEV), use_cache=False)
+    ref = torch.from_numpy(z["prefill_fp32"])
+    valid = attn_mask.bool()
+    err = (out.last_hidden_state.float().cpu() - ref).abs()[valid]
+    assert err.max() <= 6e-2 * ref[valid].abs().max()      # bf16 storage through 3 layers
