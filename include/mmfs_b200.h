@@ -168,6 +168,19 @@ int mmfs_attn_generic(const void *q, const void *k, const void *v, void *out, co
                       long q_bs, long q_ts, long k_bs, long k_ts, long v_bs, long v_ts, long o_bs, long o_ts,
                       float scale, int causal, int past, int dtype, void *stream);
 
+/*
+ * softmax(q k^T * scale + mask) v on the tensor cores (tcgen05.mma, TMEM accumulators, TMA tiles):
+ * the prefill path.  Same argument meaning as mmfs_attn_generic; requires hd in {64, 128}, dtype
+ * bf16 / f16, 16-byte aligned pointers and strides (MMFS_EUNSUPPORTED otherwise -- callers route
+ * those cases to mmfs_attn_generic).  Replaces LlamaAttention.forward's eager attention
+ * (decoders/modeling_llama_mmfs.py:246-264), CLIPXAttention.forward's xformers call
+ * (encoders/vit_adapter/xattn.py:70-72) and the SD-UNet attention (decoders/sd.py:64-65).
+ */
+int mmfs_attn_forward(const void *q, const void *k, const void *v, void *out, const uint8_t *key_mask,
+                      int B, int H, int Tq, int Tkv, int hd,
+                      long q_bs, long q_ts, long k_bs, long k_ts, long v_bs, long v_ts, long o_bs, long o_ts,
+                      float scale, int causal, int past, int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

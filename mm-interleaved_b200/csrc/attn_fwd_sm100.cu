@@ -1,0 +1,461 @@
+// attn_fwd_sm100.cu -- softmax(Q K^T * scale + mask) V on the 5th-generation tensor cores.
+//
+// Replaces, for prefill-sized problems,
+//   LlamaAttention.forward's eager path      decoders/modeling_llama_mmfs.py:246-264
+//       (matmul -> +mask -> max(finfo.min) -> fp32 softmax -> matmul, (B,40,T,T) scores materialised)
+//   CLIPXAttention.forward                   encoders/vit_adapter/xattn.py:47-141 (xformers
+//       memory_efficient_attention, non-causal, T = 257, 16 x 64)
+//   the SD-UNet self-/cross-attention        decoders/sd.py:64-65 (xformers)
+//
+// B200-first design (hand-written PTX, no CUTLASS):
+//   * one CTA per (128 query rows, head, batch entry); Q / K / V tiles arrive by TMA
+//     (cp.async.bulk.tensor.4d, SWIZZLE_128B) straight from the projection GEMM's (B, T, H, hd)
+//     layout -- no transposes, K and V double-buffered;
+//   * S = Q K^T and O += P V are tcgen05.mma (cta_group::1, kind::f16, M = 128) issued by ONE
+//     thread; accumulators live in TMEM: two S buffers (2 x 128 columns) so that S_{j+1} is
+//     computed while the softmax of S_j runs, plus the O accumulator (hd columns);
+//   * 4 softmax warps own one TMEM lane (= one query row) per thread: tcgen05.ld the scores, online
+//     softmax in fp32 with exp2, write P as bf16 into a swizzled shared-memory tile (the A operand
+//     of the second MMA), rescale O in TMEM (tcgen05.ld / tcgen05.st);
+//   * V is consumed as an MN-major B operand exactly as TMA delivers it (no transpose);
+//   * causal tiles above the diagonal are never loaded; causal / key-padding / tail masks are
+//     applied on the scores in registers; the (B,1,T,T) additive mask is never built.
+// Roofline: tensor pipe (2 * 2 * 128*128*hd flop per KV tile); the MUFU exp2 of the softmax is the
+// co-limiter (128*128 exps per tile at 16/clk/SM), see DESIGN.md.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mmfs {
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra D_%=;\n\t"
+        "bra W_%=;\n\t"
+        "D_%=:\n\t}" ::"r"(s_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+        "r"(s_addr(dst)), "l"(map), "r"(s_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::
+        "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {   // arrives on `bar` when all prior MMAs of this thread retire
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_addr(bar)) : "memory");
+}
+// 32 lanes x 32 columns of fp32: thread t of the warp gets lane (lane_base + t), columns [col, col+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::
+        "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// ---- descriptors (cute/arch/mma_sm100_desc.hpp: SmemDescriptor / InstrDescriptor bit layouts) ---------------
+//  [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 |
+//  [46,48) version = 1 (sm_100) | [61,64) layout type (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46) | (2ull << 61);
+}
+//  [4,6) D format (1 = F32) | [7,10) A format | [10,13) B format (0 = F16, 1 = BF16) | [15] A major | [16] B major
+//  (0 = K, 1 = MN) | [17,23) N >> 3 | [24,29) M >> 4
+__host__ __device__ constexpr uint32_t instr_desc(int fmt, int b_mn_major, int M, int N) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int kBM = 128, kBN = 128;
+constexpr int kAttnThreads = 192;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: softmax / epilogue
+constexpr uint32_t kTmemCols = 512; // S0 | S1 | O (<= 128)  -> power of two >= 384
+
+template <typename T> struct AttnFmt;
+template <> struct AttnFmt<__nv_bfloat16> { static constexpr int code = 1; };
+template <> struct AttnFmt<__half> { static constexpr int code = 0; };
+
+struct AttnParams {
+    void *out;                 // (B, Tq, H, hd), strides o_bs / o_ts elements
+    const uint8_t *key_mask;   // (B, Tkv) or null
+    int B, H, Tq, Tkv, causal, past;
+    long o_bs, o_ts;
+    float scale_log2e;         // scale * log2(e)
+};
+
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+    __half2 t = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+
+// Shared memory (dynamic, 1024-byte aligned): Q [HD/64 boxes][128 rows][128 B] | K [2 stages][HD/64][128][128 B] |
+// V [2][HD/64][128][128 B] | P [2 boxes][128][128 B] | barriers | tmem base | key-mask bytes [2][128]
+template <typename T, int HD>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                const __grid_constant__ CUtensorMap map_v, const AttnParams p) {
+    constexpr int NBOX = HD / 64;
+    constexpr uint32_t BOX_BYTES = 128 * 128;           // 128 rows x 128 B
+    constexpr uint32_t TILE_BYTES = NBOX * BOX_BYTES;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sQ = smem;
+    uint8_t *sK = sQ + TILE_BYTES;
+    uint8_t *sV = sK + 2 * TILE_BYTES;
+    uint8_t *sP = sV + 2 * TILE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * BOX_BYTES);
+    uint64_t *q_full = bars + 0, *k_full = bars + 1 /*[2]*/, *v_full = bars + 3 /*[2]*/, *k_empty = bars + 5 /*[2]*/,
+             *v_empty = bars + 7 /*[2]*/, *s_full = bars + 9 /*[2]*/, *p_full = bars + 11, *o_ready = bars + 12;
+    uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + 13);
+    uint8_t *s_kmask = reinterpret_cast<uint8_t *>(bars + 14);   // [2][128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = m_tile * kBM;
+    // keys this query tile can see: causal -> j <= past + q; never beyond Tkv
+    int kv_end = p.Tkv;
+    if (p.causal) kv_end = min(p.Tkv, p.past + min(q0 + kBM, p.Tq));
+    const int n_tiles = (kv_end + kBN - 1) / kBN;
+
+    if (threadIdx.x == 0) {
+        bar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) { bar_init(k_full + i, 1); bar_init(v_full + i, 1); bar_init(k_empty + i, 1); bar_init(v_empty + i, 1); bar_init(s_full + i, 1); }
+        bar_init(p_full, 128);
+        bar_init(o_ready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM allocation is a warp-wide operation; the same warp frees it at the end
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(tmem_base_smem)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+    const uint32_t tmem_s0 = tmem_base, tmem_o = tmem_base + 256;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            bar_expect_tx(q_full, TILE_BYTES);
+#pragma unroll
+            for (int bx = 0; bx < NBOX; ++bx) tma_load_4d(sQ + bx * BOX_BYTES, &map_q, q_full, bx * 64, h, q0, b);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int s = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                bar_wait(k_empty + s, ph ^ 1);
+                bar_expect_tx(k_full + s, TILE_BYTES);
+#pragma unroll
+                for (int bx = 0; bx < NBOX; ++bx)
+                    tma_load_4d(sK + s * TILE_BYTES + bx * BOX_BYTES, &map_k, k_full + s, bx * 64, h, j * kBN, b);
+                bar_wait(v_empty + s, ph ^ 1);
+                bar_expect_tx(v_full + s, TILE_BYTES);
+#pragma unroll
+                for (int bx = 0; bx < NBOX; ++bx)
+                    tma_load_4d(sV + s * TILE_BYTES + bx * BOX_BYTES, &map_v, v_full + s, bx * 64, h, j * kBN, b);
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer (one thread) ==============================
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = instr_desc(AttnFmt<T>::code, 0, kBM, kBN);   // S = Q K^T : both K-major
+            constexpr uint32_t idesc_o = instr_desc(AttnFmt<T>::code, 1, kBM, HD);    // O = P V   : V is MN-major
+            auto issue_s = [&](int j) {
+                const int s = j & 1;
+                bar_wait(k_full + s, (j >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < HD / 16; ++kk) {
+                    const uint32_t koff = (kk >> 2) * BOX_BYTES + (kk & 3) * 32;   // 64-element box, then 32 B inside the atom
+                    umma_f16(tmem_s0 + (uint32_t)s * 128u, smem_desc(s_addr(sQ) + koff, 16, 1024),
+                             smem_desc(s_addr(sK) + s * TILE_BYTES + koff, 16, 1024), idesc_s, kk > 0);
+                }
+                umma_commit(s_full + s);    // S_j complete -> softmax may read it
+                umma_commit(k_empty + s);   // ... and K stage s may be refilled
+            };
+            bar_wait(q_full, 0);
+            if (n_tiles > 0) issue_s(0);
+            for (int j = 0; j < n_tiles; ++j) {
+                if (j + 1 < n_tiles) issue_s(j + 1);     // overlaps with the softmax of tile j
+                const int s = j & 1;
+                bar_wait(p_full, j & 1);                 // P_j in smem, O rescaled
+                bar_wait(v_full + s, (j >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < kBN / 16; ++kk) {
+                    const uint32_t aoff = (kk >> 2) * BOX_BYTES + (kk & 3) * 32;   // P: K-major, K = keys
+                    const uint32_t boff = s * TILE_BYTES + kk * 16 * 128;           // V: 16 key rows of 128 B per k-step
+                    umma_f16(tmem_o, smem_desc(s_addr(sP) + aoff, 16, 1024),
+                             smem_desc(s_addr(sV) + boff, BOX_BYTES, 1024), idesc_o, (j > 0) || (kk > 0));
+                }
+                umma_commit(o_ready);
+                umma_commit(v_empty + s);
+            }
+        }
+    } else {
+        // ============================== softmax / correction / epilogue ==============================
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;          // query row within the tile == TMEM lane
+        const int tid = threadIdx.x - 64;             // 0..127 (for cooperative loads)
+        const int q_abs = q0 + row;
+        const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+        float m_run = -INFINITY, l_run = 0.f;
+        const int causal_limit = p.causal ? (p.past + q_abs) : 0x7fffffff;   // last visible key index
+        uint8_t *p_row = sP + row * 128;
+
+        for (int j = 0; j < n_tiles; ++j) {
+            const int s = j & 1;
+            const int k0 = j * kBN;
+            if (p.key_mask != nullptr) {              // stage the 128 mask bytes of this tile (double-buffered by s)
+                const int kj = k0 + tid;
+                s_kmask[s * 128 + tid] = (kj < p.Tkv) ? p.key_mask[(long)b * p.Tkv + kj] : 0;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            bar_wait(s_full + s, (j >> 1) & 1);
+            tc_fence_after();
+            const bool need_mask = (k0 + kBN - 1 > causal_limit) || (k0 + kBN > p.Tkv) || (p.key_mask != nullptr);
+            const uint32_t t_s = tmem_s0 + (uint32_t)s * 128u + lane_sel;
+
+            // pass 1: row max of the (masked) scores
+            float m_tile = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < kBN; c += 32) {
+                float v[32];
+                tmem_ld32(t_s + c, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float x = v[i];
+                    if (need_mask) {
+                        const int kj = k0 + c + i;
+                        const bool ok = (kj <= causal_limit) && (kj < p.Tkv) && (p.key_mask == nullptr || s_kmask[s * 128 + c + i]);
+                        x = ok ? x : -INFINITY;
+                    }
+                    m_tile = fmaxf(m_tile, x);
+                }
+            }
+            const float m_new = fmaxf(m_run, m_tile);
+            const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2e;
+            const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run * p.scale_log2e - m_scaled);
+
+            // the previous P V must have retired before P is overwritten and O is rescaled
+            if (j > 0) {
+                bar_wait(o_ready, (j - 1) & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < HD; c += 32) {   // O *= alpha (this thread's row)
+                    float o[32];
+                    tmem_ld32(tmem_o + lane_sel + c, o);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] *= alpha;
+                    tmem_st32(tmem_o + lane_sel + c, o);
+                }
+            }
+
+            // pass 2: P = exp2(S * scale_log2e - m), row sum, bf16 into the swizzled A-operand tile
+            float l_tile = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < kBN; c += 32) {
+                float v[32];
+                tmem_ld32(t_s + c, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float e = exp2f(v[i] * p.scale_log2e - m_scaled);
+                    if (need_mask) {
+                        const int kj = k0 + c + i;
+                        const bool ok = (kj <= causal_limit) && (kj < p.Tkv) && (p.key_mask == nullptr || s_kmask[s * 128 + c + i]);
+                        e = ok ? e : 0.f;
+                    }
+                    v[i] = e;
+                    l_tile += e;
+                }
+                // 32 keys = 64 B = 4 chunks of 16 B; box = c / 64, chunk index within the 128-B row = (c % 64)/8 + q
+                uint8_t *box_row = p_row + (c >> 6) * BOX_BYTES;
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    const int chunk = ((c & 63) >> 3) + qd;
+                    const int phys = chunk ^ (row & 7);                       // SWIZZLE_128B
+                    uint4 w;
+                    w.x = pack2<T>(v[qd * 8 + 0], v[qd * 8 + 1]);
+                    w.y = pack2<T>(v[qd * 8 + 2], v[qd * 8 + 3]);
+                    w.z = pack2<T>(v[qd * 8 + 4], v[qd * 8 + 5]);
+                    w.w = pack2<T>(v[qd * 8 + 6], v[qd * 8 + 7]);
+                    *reinterpret_cast<uint4 *>(box_row + phys * 16) = w;
+                }
+            }
+            l_run = l_run * alpha + l_tile;
+            m_run = m_new;
+            fence_async_smem();        // generic-proxy writes of P -> visible to the tensor core (async proxy)
+            tc_fence_before();
+            bar_arrive(p_full);
+        }
+
+        // epilogue: O / l -> global
+        if (n_tiles > 0) {
+            bar_wait(o_ready, (n_tiles - 1) & 1);
+            tc_fence_after();
+        }
+        const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;   // fully masked row -> zeros
+        if (q_abs < p.Tq) {
+            T *op = static_cast<T *>(p.out) + (long)b * p.o_bs + (long)q_abs * p.o_ts + (long)h * HD;
+#pragma unroll 1
+            for (int c = 0; c < HD; c += 32) {
+                float o[32];
+                if (n_tiles > 0) tmem_ld32(tmem_o + lane_sel + c, o);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = 0.f;
+                }
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    uint4 w;
+                    w.x = pack2<T>(o[qd * 8 + 0] * inv, o[qd * 8 + 1] * inv);
+                    w.y = pack2<T>(o[qd * 8 + 2] * inv, o[qd * 8 + 3] * inv);
+                    w.z = pack2<T>(o[qd * 8 + 4] * inv, o[qd * 8 + 5] * inv);
+                    w.w = pack2<T>(o[qd * 8 + 6] * inv, o[qd * 8 + 7] * inv);
+                    *reinterpret_cast<uint4 *>(op + c + qd * 8) = w;
+                }
+            }
+        } else if (n_tiles > 0) {   // rows past Tq still take part in the warp-collective TMEM loads
+#pragma unroll 1
+            for (int c = 0; c < HD; c += 32) { float o[32]; tmem_ld32(tmem_o + lane_sel + c, o); }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// (B, T, H, hd) tensor with element strides bs / ts (heads dense): dims innermost-first {hd, H, T, B}
+static int make_map(CUtensorMap *map, const void *ptr, int dtype, int B, int T, int H, int hd, long bs, long ts, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("attn: cuTensorMapEncodeTiled is not available from this driver"); return MMFS_ECUDA; }
+    const cuuint64_t dims[4] = {(cuuint64_t)hd, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)hd * 2, (cuuint64_t)ts * 2, (cuuint64_t)bs * 2};
+    const cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, dtype == MMFS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                    const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("attn: cuTensorMapEncodeTiled failed (%d)", (int)r); return MMFS_ECUDA; }
+    return MMFS_OK;
+}
+
+template <typename T, int HD>
+static int launch_attn(const CUtensorMap &mq, const CUtensorMap &mk, const CUtensorMap &mv, const AttnParams &p, cudaStream_t st) {
+    constexpr size_t smem = 1024 + (size_t)(HD / 64) * 128 * 128 * 5 + 2 * 128 * 128 + 14 * 8 + 2 * 128 + 64;
+    auto kern = attn_fwd_kernel<T, HD>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MMFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    dim3 grid((p.Tq + kBM - 1) / kBM, p.H, p.B);
+    kern<<<grid, kAttnThreads, smem, st>>>(mq, mk, mv, p);
+    MMFS_CUDA(cudaGetLastError());
+    return MMFS_OK;
+}
+
+}  // namespace mmfs
+
+using namespace mmfs;
+
+extern "C" int mmfs_attn_forward(const void *q, const void *k, const void *v, void *out, const uint8_t *key_mask,
+                                 int B, int H, int Tq, int Tkv, int hd,
+                                 long q_bs, long q_ts, long k_bs, long k_ts, long v_bs, long v_ts, long o_bs, long o_ts,
+                                 float scale, int causal, int past, int dtype, void *stream) {
+    MMFS_CHECK_ARG(B >= 0 && H > 0 && Tq >= 0 && Tkv > 0, "attn_forward: bad shape");
+    if (B == 0 || Tq == 0) return MMFS_OK;
+    MMFS_CHECK_ARG(q && k && v && out, "attn_forward: null pointer argument");
+    if (!(hd == 64 || hd == 128) || !(dtype == MMFS_BF16 || dtype == MMFS_F16)) {
+        set_error("attn_forward: tensor-core path needs hd in {64,128} and bf16/f16 (got hd=%d dtype=%d)", hd, dtype);
+        return MMFS_EUNSUPPORTED;
+    }
+    if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) % 16 != 0 ||
+        (q_bs | q_ts | k_bs | k_ts | v_bs | v_ts | o_bs | o_ts) % 8 != 0 || B > 65535 || H > 65535) {
+        set_error("attn_forward: pointers / strides must be 16-byte aligned; B, H <= 65535");
+        return MMFS_EUNSUPPORTED;
+    }
+    CUtensorMap mq, mk, mv;
+    int rc;
+    if ((rc = make_map(&mq, q, dtype, B, Tq, H, hd, q_bs, q_ts, kBM)) != MMFS_OK) return rc;
+    if ((rc = make_map(&mk, k, dtype, B, Tkv, H, hd, k_bs, k_ts, kBN)) != MMFS_OK) return rc;
+    if ((rc = make_map(&mv, v, dtype, B, Tkv, H, hd, v_bs, v_ts, kBN)) != MMFS_OK) return rc;
+    AttnParams p;
+    p.out = out; p.key_mask = key_mask; p.B = B; p.H = H; p.Tq = Tq; p.Tkv = Tkv; p.causal = causal; p.past = past;
+    p.o_bs = o_bs; p.o_ts = o_ts; p.scale_log2e = scale * 1.4426950408889634f;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MMFS_BF16) return hd == 64 ? launch_attn<__nv_bfloat16, 64>(mq, mk, mv, p, st) : launch_attn<__nv_bfloat16, 128>(mq, mk, mv, p, st);
+    return hd == 64 ? launch_attn<__half, 64>(mq, mk, mv, p, st) : launch_attn<__half, 128>(mq, mk, mv, p, st);
+}

@@ -1,0 +1,79 @@
+"""GPU parity of the tcgen05 attention kernel against an fp32 PyTorch statement of
+softmax(q k^T / sqrt(d) + mask) v on the same bf16/f16-rounded inputs.
+
+Tolerance: |err| <= 2e-2 * max|ref| per tensor and mean |err| <= 2e-3 * max|ref| (P is rounded to the 16-bit
+type before the second MMA, as in the reference where `attn_weights.to(query_states.dtype)` precedes
+the PV matmul, decoders/modeling_llama_mmfs.py:261-262)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def eager(q, k, v, km, causal, past):
+    B, Tq, H, hd = q.shape
+    Tkv = k.shape[1]
+    s = torch.einsum("bqhd,bkhd->bhqk", q.float() * hd ** -0.5, k.float())
+    allow = torch.ones((B, 1, Tq, Tkv), dtype=torch.bool, device=q.device)
+    if km is not None:
+        allow = allow & km[:, None, None, :].bool()
+    if causal:
+        allow = allow & (torch.arange(Tkv, device=q.device)[None, :] <= past + torch.arange(Tq, device=q.device)[:, None])[None, None]
+    s = s.masked_fill(~allow, float("-inf"))
+    p = torch.softmax(s, -1).nan_to_num(0.0)
+    return torch.einsum("bhqk,bkhd->bqhd", p, v.float())
+
+
+CASES = [
+    # B, H, Tq, Tkv, hd, causal, past, masked
+    (1, 2, 128, 128, 128, False, 0, False),
+    (1, 2, 128, 128, 64, False, 0, False),
+    (2, 3, 256, 256, 128, True, 0, False),
+    (1, 4, 257, 257, 64, False, 0, False),      # CLIP ViT-L/14: 257 tokens, 16 x 64
+    (2, 2, 200, 200, 128, True, 0, True),       # ragged + key padding (left-padded batch)
+    (1, 2, 96, 352, 128, True, 256, True),      # chunked prefill on top of a cache
+    (1, 5, 512, 512, 128, True, 0, False),      # cfg 2 prefill length
+    (1, 2, 1024, 77, 64, False, 0, False),      # SD cross-attention: kv = 77
+    (1, 2, 2048, 2048, 128, True, 0, False),    # cfg 3 prefill length
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_tc_attention_matches_eager(case, dtype):
+    from mm_interleaved_b200 import attn_tc, ops
+    B, H, Tq, Tkv, hd, causal, past, masked = CASES[case]
+    g = torch.Generator().manual_seed(case)
+    qkv_q = torch.randn((B, Tq, 3, H, hd), generator=g).to(dtype).to(DEV)       # q is a strided view, like the model's
+    q = qkv_q[:, :, 0]
+    k = torch.randn((B, Tkv, H, hd), generator=g).to(dtype).to(DEV)
+    v = torch.randn((B, Tkv, H, hd), generator=g).to(dtype).to(DEV)
+    km = None
+    if masked:
+        km = torch.ones((B, Tkv), dtype=torch.uint8, device=DEV)
+        km[0, :5] = 0
+        km[-1, 7:19] = 0
+    assert attn_tc.supported(q, k, v, Tq, Tkv, hd)
+    out = ops.attention(q, k, v, key_mask=km, causal=causal, past=past).view(B, Tq, H, hd)
+    torch.cuda.synchronize()
+    ref = eager(q, k, v, km, causal, past)
+    err = (out.float() - ref).abs()
+    scale = ref.abs().max()
+    assert torch.isfinite(out.float()).all()
+    assert err.max() <= 2e-2 * scale, (err.max().item(), scale.item())
+    assert err.mean() <= 2e-3 * scale
+    # and the bandwidth kernel agrees on the same problem
+    out_g = ops.attention(q, k, v, key_mask=km, causal=causal, past=past, force_generic=True).view(B, Tq, H, hd)
+    assert (out_g.float() - ref).abs().max() <= 2e-2 * scale
+
+
+def test_unsupported_shapes_fall_to_the_bandwidth_kernel_and_errors_are_loud():
+    from mm_interleaved_b200 import _lib, attn_tc
+    q = torch.randn((1, 64, 2, 80), device=DEV, dtype=torch.bfloat16)
+    assert not attn_tc.supported(q, q, q, 64, 64, 80)
+    lib = _lib.lib()
+    rc = lib.mmfs_attn_forward(q.data_ptr(), q.data_ptr(), q.data_ptr(), q.data_ptr(), None, 1, 2, 64, 64, 80,
+                               q.stride(0), q.stride(1), q.stride(0), q.stride(1), q.stride(0), q.stride(1), q.stride(0), q.stride(1),
+                               0.1, 0, 0, _lib.BF16, None)
+    assert rc == _lib.EUNSUPPORTED
