@@ -346,16 +346,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             tc_fence_after();
         }
         const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;   // fully masked row -> zeros
-        if (q_abs < p.Tq) {
-            T *op = static_cast<T *>(p.out) + (long)b * p.o_bs + (long)q_abs * p.o_ts + (long)h * HD;
+        // tcgen05.ld is warp-collective (.sync.aligned): every lane executes it, rows past Tq only skip the store
+        T *op = static_cast<T *>(p.out) + (long)b * p.o_bs + (long)q_abs * p.o_ts + (long)h * HD;
 #pragma unroll 1
-            for (int c = 0; c < HD; c += 32) {
-                float o[32];
-                if (n_tiles > 0) tmem_ld32(tmem_o + lane_sel + c, o);
-                else {
+        for (int c = 0; c < HD; c += 32) {
+            float o[32];
+            if (n_tiles > 0) {           // CTA-uniform
+                tmem_ld32(tmem_o + lane_sel + c, o);
+            } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) o[i] = 0.f;
-                }
+                for (int i = 0; i < 32; ++i) o[i] = 0.f;
+            }
+            if (q_abs < p.Tq) {
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
                     uint4 w;
@@ -366,9 +368,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     *reinterpret_cast<uint4 *>(op + c + qd * 8) = w;
                 }
             }
-        } else if (n_tiles > 0) {   // rows past Tq still take part in the warp-collective TMEM loads
-#pragma unroll 1
-            for (int c = 0; c < HD; c += 32) { float o[32]; tmem_ld32(tmem_o + lane_sel + c, o); }
+            __syncwarp();
         }
     }
 

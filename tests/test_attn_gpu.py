@@ -41,6 +41,7 @@ CASES = [
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.timeout(60)
 def test_tc_attention_matches_eager(case, dtype):
     from mm_interleaved_b200 import attn_tc, ops
     B, H, Tq, Tkv, hd, causal, past, masked = CASES[case]
