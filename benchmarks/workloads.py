@@ -208,8 +208,244 @@ def cpu_baseline_msda(wl, layers=1, threads=None):
                       f"scaled x{wl.LAYERS} layers"}
 
 
-WORKLOADS = {"msda_cfg3": MsdaCfg3}
-AUTO = "msda_cfg3"
+class InterleavedCfg3(Workload):
+    """BASELINE cfg 3: the interleaved image-text forward on 4-image / 2048-token sequences, bf16 -- embed
+    splice + image-visibility mask + MMFS feature packing (mm_interleaved.py:121-252), the 40-layer
+    Llama-13B decoder with MMFS cross-attention in every 4th layer (modeling_llama_mmfs.py:623-752) and the
+    text head (decoder_text.py:140-163), i.e. the body of MMInterleaved.forward up to the logits.  The
+    visual tokenizer (CLIP ViT-L/14 + ViT-Adapter + Q-Former, ~1.3 % of the step's FLOPs) is not built yet:
+    its outputs (vis_embed, multiscale_features) are synthetic inputs of the step -- stated in
+    config.workload.  Random-init weights of the real architecture, synthetic token layout of SURVEY.md 8d."""
+
+    name = "interleaved_cfg3"
+    T, N_IMG, TOK_PER_IMG = 2048, 4, 64
+    SOI_AT = (1, 512, 1024, 1536)
+    EXTRA_BOS_AT = 1023
+    LAYERS_CROSS, LAYERS_TOTAL = 10, 40
+
+    def _config(self):
+        from mm_interleaved_b200.llama_mmfs import LlamaMMFSConfig
+        return LlamaMMFSConfig()
+
+    def make_host_inputs(self, pin):
+        B = self.local_batch or 4
+        self.B = B
+        g = torch.Generator().manual_seed(4321 + self.rank)
+        ids = torch.randint(3, 31999, (B, self.T), generator=g)
+        ids[:, 0] = 1
+        for s in self.SOI_AT:
+            ids[:, s] = 32001
+            ids[:, s + 1:s + 1 + self.TOK_PER_IMG] = 32000
+        ids[:, self.EXTRA_BOS_AT] = 1
+        dt = torch.bfloat16
+        vis = (0.5 * torch.randn((B * self.N_IMG, self.TOK_PER_IMG, 5120), generator=g)).to(dt)
+        feats = [torch.randn((B * self.N_IMG, 1024, s, s), generator=g).to(dt) for s in (32, 16, 8)]
+        host = [ids, vis] + feats
+        self.host = [t.pin_memory() for t in host] if pin else host
+
+    def setup(self):
+        import mm_interleaved_b200 as m
+        from mm_interleaved_b200 import ops, sampler
+        from mm_interleaved_b200.mm_interleaved import InterleavedForward
+        from mm_interleaved_b200.mmfs import MMFS
+        self.m, self.ops = m, ops
+        self.make_host_inputs(pin=True)
+        cfg = self._config()
+        self.cfg = cfg
+        with torch.device("meta"):
+            model = InterleavedForward(cfg).to(torch.bfloat16)
+        model = model.to_empty(device="cuda")
+        gen = torch.Generator(device="cuda").manual_seed(7)
+        with torch.no_grad():
+            for name, p in model.named_parameters():
+                if name.endswith("norm.weight") or name.endswith("layernorm.weight") or ".norm1." in name or ".norm2." in name:
+                    p.fill_(1.0)
+                elif name.endswith(".gate"):
+                    p.fill_(0.5)
+                elif name.endswith("sampling_offsets.bias"):
+                    p.uniform_(-3.0, 3.0, generator=gen)                     # mmfs.py:103-110
+                elif name.endswith("ignore_token") or name.endswith(".bias"):
+                    p.zero_()
+                elif name.endswith("sampling_offsets.weight"):
+                    p.normal_(0.0, 0.004, generator=gen)
+                else:
+                    p.normal_(0.0, 0.02, generator=gen)
+            for mod in model.modules():
+                if isinstance(mod, MMFS):
+                    mod.scale_ratios = torch.tensor(mod._scale_list, device="cuda")
+        self.model = model.eval()
+        self.dev = [t.cuda() for t in self.host]
+        self.nimg = torch.full((self.B,), self.N_IMG, dtype=torch.long, device="cuda")
+        self.out_h = torch.empty((self.B, self.T), dtype=torch.long).pin_memory()
+        self.last = None
+        # time the dominant hand-written kernels with CUDA events from inside the step
+        self._sampler_events, self._attn_events = [], []
+        orig_sampler, orig_attn = sampler.mmfs_sampler_forward, ops.attention
+
+        def timed_sampler(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = orig_sampler(*a, **k); e1.record()
+            self._sampler_events.append((e0, e1)); self._launches += 1
+            return r
+
+        def timed_attn(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = orig_attn(*a, **k); e1.record()
+            self._attn_events.append((e0, e1))
+            return r
+
+        sampler.mmfs_sampler_forward = timed_sampler
+        import mm_interleaved_b200.mmfs as mmfs_mod
+        mmfs_mod._sampler.mmfs_sampler_forward = timed_sampler
+        import mm_interleaved_b200.llama_mmfs as lm
+        lm.ops.attention = timed_attn
+        self.reset_counters()
+
+    def reset_counters(self):
+        super().reset_counters()
+        self._sampler_events, self._attn_events = [], []
+        if hasattr(self, "ops"):
+            self.ops.launch_counter[0] = 0
+
+    def launch_count(self):
+        return self._launches + self.ops.launch_counter[0]
+
+    def units_per_step(self):
+        return self.B
+
+    def _forward(self, tensors):
+        ids, vis = tensors[0], tensors[1]
+        with torch.no_grad():
+            logits = self.model(ids, {"vis_embed": vis, "multiscale_features": tensors[2:]}, self.nimg, self.N_IMG)
+            return logits.argmax(-1)
+
+    def step_device(self):
+        self.last = self._forward(self.dev)
+
+    def step_e2e(self):
+        dev = [t.to("cuda", non_blocking=True) for t in self.host]
+        pred = self._forward(dev)
+        self.out_h.copy_(pred, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.last = pred
+
+    def result_checksum(self):
+        return self.last.sum().reshape(1).float()
+
+    def h2d_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self.host)
+
+    def d2h_bytes(self):
+        return self.out_h.numel() * self.out_h.element_size()
+
+    def kernel_stats(self):
+        torch.cuda.synchronize()
+        s = [a.elapsed_time(b) for a, b in self._sampler_events]
+        t = [a.elapsed_time(b) for a, b in self._attn_events]
+        return {"launches": len(s), "avg_ms": sum(s) / len(s) if s else None,
+                "attn_launches": len(t), "attn_avg_ms": sum(t) / len(t) if t else None}
+
+    def config(self):
+        return {"workload": f"BASELINE cfg3 interleaved forward, {self.B} sequences/GPU x (4 images, 2048 tokens): embed splice + "
+                            "visibility mask + MMFS feature packing + Llama-13B decoder (40 layers, MMFS cross-attn every 4th) "
+                            "+ text head + argmax; visual-tokenizer outputs (vis_embed, 3 multi-scale maps) are synthetic "
+                            "inputs (tokenizer not built yet)",
+                "step_unit": "one 4-image/2048-token sequence forward",
+                "global_batch": self.B * self.world, "seq_len": self.T, "images_per_seq": self.N_IMG,
+                "parallelism": f"dp{self.world}", "params": "13B Llama + 10 MMFS layers, random init, bf16",
+                "l2": "192 MiB buffer written between timed steps (L2 flush); weights (27 GB) exceed L2 anyway"}
+
+    def roofline(self, kernel):
+        peaks = measured_peaks()
+        S, M, D, L, Lq, P = 5376, 16, 64, 12, self.T, 8
+        ab = msda_algorithmic_bytes(self.B, S, M, D, L, Lq, P, 2)            # SURVEY.md 8d figure (34.1 MB / layer / sequence)
+        C = M * P * 2 + M * 3 * (P + 1)
+        fused = 2 * (self.B * S * M * D + self.B * Lq * C + 50 * C + self.B * Lq * M * D) + self.B * 4 * Lq
+        t = kernel["avg_ms"] * 1e-3 if kernel["avg_ms"] else None
+        achieved = ab / t / 1e9 if t else None
+        flops = 4.0 * self.B * self.T * self.T * 5120 / 2                     # causal QK^T + PV per layer
+        ta = kernel["attn_avg_ms"] * 1e-3 if kernel.get("attn_avg_ms") else None
+        return {"kernel": "mmfs_sampler_kernel<bf16,64> (fused MMFS deform-attn sampler)", "bound": "hbm",
+                "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"] if achieved else None,
+                "algorithmic_bytes_per_launch": ab, "fused_kernel_bytes_per_launch": fused,
+                "achieved_fused_bytes_GBs": fused / t / 1e9 if t else None,
+                "avg_launch_us": t * 1e6 if t else None, "launches_timed": kernel["launches"], "traffic": None,
+                "attention": {"kernel": "attn_fwd_kernel<bf16,128> (tcgen05)", "bound": "tensor",
+                              "achieved": flops / ta / 1e12 if ta else None, "peak": peaks["bf16_tflops_sustained"],
+                              "unit": "TFLOP/s", "frac": flops / ta / 1e12 / peaks["bf16_tflops_sustained"] if ta else None,
+                              "flops_per_launch": flops, "avg_launch_us": ta * 1e6 if ta else None,
+                              "launches_timed": kernel.get("attn_launches")}}
+
+    # ---- CPU baseline / reference arm: oracle restatement of the reference forward, bounded sample ----
+    def setup_cpu_only(self):
+        self.local_batch = 1
+        self.make_host_inputs(pin=False)
+
+    def _cpu_layer_weights(self, cross, seed):
+        import mm_interleaved_b200  # noqa: F401
+        from mm_interleaved_b200.llama_mmfs import LlamaDecoderLayer
+        cfg = self._config()
+        layer = LlamaDecoderLayer(cfg, cross, 0)
+        g = torch.Generator().manual_seed(seed)
+        sd = {}
+        for k, v in layer.state_dict().items():
+            if k.endswith("norm.weight") or k.endswith("layernorm.weight") or ".norm1." in k or ".norm2." in k:
+                sd["layers.0." + k] = torch.ones_like(v)
+            elif k.endswith(".gate"):
+                sd["layers.0." + k] = torch.full_like(v, 0.5)
+            elif k.endswith("sampling_offsets.bias"):
+                sd["layers.0." + k] = torch.rand(v.shape, generator=g) * 6 - 3
+            elif k.endswith(".bias") or k.endswith("ignore_token"):
+                sd["layers.0." + k] = torch.zeros_like(v)
+            else:
+                sd["layers.0." + k] = torch.randn(v.shape, generator=g) * 0.02
+        return sd
+
+    def reference_step(self):
+        """Bounded CPU sample: ONE plain decoder layer + ONE MMFS cross-attention layer of ONE sequence (T = 2048,
+        4 images, fp32) through the oracle restatement of the reference (oracle/llama.py, oracle/mmfs.py)."""
+        from oracle.llama import additive_mask_ref, llama_layer_ref
+        from mm_interleaved_b200.mm_interleaved import cross_attention_mask_from_ids, pack_mmfs_features
+        if not hasattr(self, "_cpu"):
+            ids = self.host[0][:1]
+            x = torch.randn((1, self.T, 5120), generator=torch.Generator().manual_seed(5)) * 0.5
+            feats = pack_mmfs_features([f[:4].float() for f in self.host[2:]], [32, 16, 8], torch.tensor([4]), 4)
+            cross = cross_attention_mask_from_ids(ids, 4, 1, 32001, torch.tensor([4]))
+            cfg = dict(eps=1e-6, n_heads=40, n_layers=1, spatial_shapes=[(32, 32), (16, 16), (8, 8)])
+            add_mask = additive_mask_ref(torch.ones((1, self.T)), self.T, 0, torch.float32)
+            pos = torch.arange(self.T)[None]
+            self._cpu = (x, feats, cross, cfg, add_mask, pos, self._cpu_layer_weights(False, 1), self._cpu_layer_weights(True, 2))
+        x, feats, cross, cfg, add_mask, pos, w_plain, w_cross = self._cpu
+        with torch.no_grad():
+            t0 = time.time()
+            llama_layer_ref(w_plain, 0, x, None, None, add_mask, pos, cfg)
+            t1 = time.time()
+            llama_layer_ref(w_cross, 0, x, feats, cross, add_mask, pos, cfg)
+            t2 = time.time()
+        self._cpu_times = (t1 - t0, t2 - t1)
+        return self._cpu_times
+
+    # one reference step covers 2 of the 40 layers; scaled as 30 plain + 10 cross layers (head + glue excluded,
+    # < 2 % of the work), see reference_sample
+    reference_step_fraction = None
+    reference_sample = ("each step = 1 plain + 1 MMFS cross-attention decoder layer of 1 sequence (T=2048, 4 images) in fp32 "
+                        "through the oracle restatement; value = 1 / (30*t_plain + 10*t_cross)")
+
+    def cpu_baseline(self):
+        threads = min(os.cpu_count() or 1, 64)
+        torch.set_num_threads(threads)
+        if not hasattr(self, "host_cpu_ready"):
+            self.host_cpu_ready = True
+        tp, tc = self.reference_step()
+        tp, tc = self.reference_step()
+        return {"value": 1.0 / (30 * tp + 10 * tc), "unit": self.unit, "cores": threads, "kind": "port",
+                "sample": f"1 plain layer ({tp:.2f} s) + 1 MMFS cross layer ({tc:.2f} s) of 1 sequence, fp32, oracle "
+                          "restatement of the reference forward; scaled to 30 plain + 10 cross layers"}
+
+
+WORKLOADS = {"msda_cfg3": MsdaCfg3, "interleaved_cfg3": InterleavedCfg3}
+AUTO = "interleaved_cfg3"
 
 
 def make(name, rank, world, local_batch):
@@ -227,13 +463,22 @@ def run_reference_arm(args, world):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     wl.setup_cpu_only()
-    for _ in range(max(args.warmup, 1)):
+    if name == "interleaved_cfg3":
+        threads = min(threads, 64)
+        torch.set_num_threads(threads)
+    for _ in range(max(min(args.warmup, 2), 1)):
         wl.reference_step()
     t0 = time.time()
+    acc = [0.0, 0.0]
     for _ in range(args.steps):
-        wl.reference_step()
+        r = wl.reference_step()
+        if wl.reference_step_fraction is None:
+            acc[0] += r[0]; acc[1] += r[1]
     dt = time.time() - t0
-    value = wl.reference_step_fraction * args.steps / dt
+    if wl.reference_step_fraction is None:
+        value = 1.0 / (30 * acc[0] / args.steps + 10 * acc[1] / args.steps)
+    else:
+        value = wl.reference_step_fraction * args.steps / dt
     cfg = wl.config()
     return {"impl": "reference", "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": dt * 1e3 / args.steps,

@@ -64,6 +64,7 @@ class MMFS(nn.Module):
         self.offset_init_magnitude = offset_init_magnitude
         self.max_num_image_per_seq = max_num_image_per_seq
         assert len(spatial_shapes) == n_levels
+        self._scale_list = [s / base_spatial_shape for s in spatial_shapes]   # to rebuild the buffer after to_empty()
         self.register_buffer("scale_ratios", torch.tensor([s / base_spatial_shape for s in spatial_shapes]),
                              persistent=False)
         d_inner = int(d_model * ratio)
