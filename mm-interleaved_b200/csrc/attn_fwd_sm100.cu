@@ -113,9 +113,10 @@ __host__ __device__ constexpr uint32_t instr_desc(int fmt, int b_mn_major, int M
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-constexpr int kBM = 128, kBN = 128;
+constexpr int kBM = 128, kBN = 64;  // 64-key tiles: 112 KB of shared memory and 256 TMEM columns per CTA -> 2 CTAs / SM
 constexpr int kAttnThreads = 192;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: softmax / epilogue
-constexpr uint32_t kTmemCols = 512; // S0 | S1 | O (<= 128)  -> power of two >= 384
+constexpr uint32_t kTmemCols = 256; // S0 (64) | S1 (64) | O (<= 128)
+constexpr float kRescaleThreshold = 8.f;   // lazy O rescale: only when the running max grows by > 2^8 (exact, see below)
 
 template <typename T> struct AttnFmt;
 template <> struct AttnFmt<__nv_bfloat16> { static constexpr int code = 1; };
@@ -138,27 +139,57 @@ template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) 
     __half2 t = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&t);
 }
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// two back-to-back 32-column TMEM loads, one wait
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+    uint32_t r[64];
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+        uint32_t *q = r + 32 * hlf;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]), "=r"(q[9]),
+              "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]), "=r"(q[17]), "=r"(q[18]),
+              "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]), "=r"(q[25]), "=r"(q[26]), "=r"(q[27]),
+              "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+            : "r"(taddr + 32u * hlf));
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
 
-// Shared memory (dynamic, 1024-byte aligned): Q [HD/64 boxes][128 rows][128 B] | K [2 stages][HD/64][128][128 B] |
-// V [2][HD/64][128][128 B] | P [2 boxes][128][128 B] | barriers | tmem base | key-mask bytes [2][128]
+// Shared memory (dynamic, 1024-byte aligned):
+//   Q [HD/64 boxes][128 rows][128 B] | K [2 stages][HD/64][64][128 B] | V [2][HD/64][64][128 B] | P [128][128 B] |
+//   barriers | tmem base | key-mask bytes [2][64]
 template <typename T, int HD>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const __grid_constant__ CUtensorMap map_v, const AttnParams p) {
     constexpr int NBOX = HD / 64;
-    constexpr uint32_t BOX_BYTES = 128 * 128;           // 128 rows x 128 B
-    constexpr uint32_t TILE_BYTES = NBOX * BOX_BYTES;
+    constexpr uint32_t QBOX_BYTES = kBM * 128;           // 128 rows x 128 B
+    constexpr uint32_t KBOX_BYTES = kBN * 128;           // 64 rows x 128 B
+    constexpr uint32_t Q_BYTES = NBOX * QBOX_BYTES;
+    constexpr uint32_t KV_BYTES = NBOX * KBOX_BYTES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *sQ = smem;
-    uint8_t *sK = sQ + TILE_BYTES;
-    uint8_t *sV = sK + 2 * TILE_BYTES;
-    uint8_t *sP = sV + 2 * TILE_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * BOX_BYTES);
+    // SWIZZLE_128B tiles need 1024-byte alignment; the dynamic window starts at offset 0 of the CTA's shared
+    // memory (no static __shared__ in this kernel), which the __align__ above requests.  No slack is added on
+    // purpose: 2 CTAs of 115 KB must fit in 227 KB.
+    if ((s_addr(smem_raw) & 1023u) != 0u) { asm volatile("trap;"); }
+    uint8_t *sQ = smem_raw;
+    uint8_t *sK = sQ + Q_BYTES;
+    uint8_t *sV = sK + 2 * KV_BYTES;
+    uint8_t *sP = sV + 2 * KV_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + QBOX_BYTES);
     uint64_t *q_full = bars + 0, *k_full = bars + 1 /*[2]*/, *v_full = bars + 3 /*[2]*/, *k_empty = bars + 5 /*[2]*/,
              *v_empty = bars + 7 /*[2]*/, *s_full = bars + 9 /*[2]*/, *p_full = bars + 11, *o_ready = bars + 12;
     uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + 13);
-    uint8_t *s_kmask = reinterpret_cast<uint8_t *>(bars + 14);   // [2][128]
+    uint8_t *s_kmask = reinterpret_cast<uint8_t *>(bars + 14);   // [2][64]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -183,27 +214,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
-    const uint32_t tmem_s0 = tmem_base, tmem_o = tmem_base + 256;
+    const uint32_t tmem_s0 = tmem_base, tmem_o = tmem_base + 2 * kBN;
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
         if (lane == 0) {
-            bar_expect_tx(q_full, TILE_BYTES);
+            bar_expect_tx(q_full, Q_BYTES);
 #pragma unroll
-            for (int bx = 0; bx < NBOX; ++bx) tma_load_4d(sQ + bx * BOX_BYTES, &map_q, q_full, bx * 64, h, q0, b);
+            for (int bx = 0; bx < NBOX; ++bx) tma_load_4d(sQ + bx * QBOX_BYTES, &map_q, q_full, bx * 64, h, q0, b);
             for (int j = 0; j < n_tiles; ++j) {
                 const int s = j & 1;
                 const uint32_t ph = (j >> 1) & 1;
                 bar_wait(k_empty + s, ph ^ 1);
-                bar_expect_tx(k_full + s, TILE_BYTES);
+                bar_expect_tx(k_full + s, KV_BYTES);
 #pragma unroll
                 for (int bx = 0; bx < NBOX; ++bx)
-                    tma_load_4d(sK + s * TILE_BYTES + bx * BOX_BYTES, &map_k, k_full + s, bx * 64, h, j * kBN, b);
+                    tma_load_4d(sK + s * KV_BYTES + bx * KBOX_BYTES, &map_k, k_full + s, bx * 64, h, j * kBN, b);
                 bar_wait(v_empty + s, ph ^ 1);
-                bar_expect_tx(v_full + s, TILE_BYTES);
+                bar_expect_tx(v_full + s, KV_BYTES);
 #pragma unroll
                 for (int bx = 0; bx < NBOX; ++bx)
-                    tma_load_4d(sV + s * TILE_BYTES + bx * BOX_BYTES, &map_v, v_full + s, bx * 64, h, j * kBN, b);
+                    tma_load_4d(sV + s * KV_BYTES + bx * KBOX_BYTES, &map_v, v_full + s, bx * 64, h, j * kBN, b);
             }
         }
     } else if (warp == 1) {
@@ -217,9 +248,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < HD / 16; ++kk) {
-                    const uint32_t koff = (kk >> 2) * BOX_BYTES + (kk & 3) * 32;   // 64-element box, then 32 B inside the atom
-                    umma_f16(tmem_s0 + (uint32_t)s * 128u, smem_desc(s_addr(sQ) + koff, 16, 1024),
-                             smem_desc(s_addr(sK) + s * TILE_BYTES + koff, 16, 1024), idesc_s, kk > 0);
+                    // 64-element box along hd, then 32 B inside the 128-byte swizzle atom
+                    umma_f16(tmem_s0 + (uint32_t)s * kBN,
+                             smem_desc(s_addr(sQ) + (kk >> 2) * QBOX_BYTES + (kk & 3) * 32, 16, 1024),
+                             smem_desc(s_addr(sK) + s * KV_BYTES + (kk >> 2) * KBOX_BYTES + (kk & 3) * 32, 16, 1024),
+                             idesc_s, kk > 0);
                 }
                 umma_commit(s_full + s);    // S_j complete -> softmax may read it
                 umma_commit(k_empty + s);   // ... and K stage s may be refilled
@@ -229,15 +262,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             for (int j = 0; j < n_tiles; ++j) {
                 if (j + 1 < n_tiles) issue_s(j + 1);     // overlaps with the softmax of tile j
                 const int s = j & 1;
-                bar_wait(p_full, j & 1);                 // P_j in smem, O rescaled
+                bar_wait(p_full, j & 1);                 // P_j in smem, O rescaled if needed
                 bar_wait(v_full + s, (j >> 1) & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < kBN / 16; ++kk) {
-                    const uint32_t aoff = (kk >> 2) * BOX_BYTES + (kk & 3) * 32;   // P: K-major, K = keys
-                    const uint32_t boff = s * TILE_BYTES + kk * 16 * 128;           // V: 16 key rows of 128 B per k-step
-                    umma_f16(tmem_o, smem_desc(s_addr(sP) + aoff, 16, 1024),
-                             smem_desc(s_addr(sV) + boff, BOX_BYTES, 1024), idesc_o, (j > 0) || (kk > 0));
+                    // P: K-major, K = keys (one 64-key box).  V: MN-major, 16 key rows of 128 B per k-step,
+                    // hd halves KBOX_BYTES apart (LBO)
+                    umma_f16(tmem_o, smem_desc(s_addr(sP) + kk * 32, 16, 1024),
+                             smem_desc(s_addr(sV) + s * KV_BYTES + kk * 16 * 128, KBOX_BYTES, 1024), idesc_o, (j > 0) || (kk > 0));
                 }
                 umma_commit(o_ready);
                 umma_commit(v_empty + s);
@@ -250,50 +283,66 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int tid = threadIdx.x - 64;             // 0..127 (for cooperative loads)
         const int q_abs = q0 + row;
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-        float m_run = -INFINITY, l_run = 0.f;
+        // m_ref: the maximum the exponentials are taken against.  It follows the true running maximum
+        // lazily -- only when that grew by more than 2^kRescaleThreshold -- which is exact (O and l are
+        // rescaled consistently, p <= 2^8 fits bf16/f16) and saves most TMEM round trips on O.
+        float m_ref = -INFINITY, l_run = 0.f;
         const int causal_limit = p.causal ? (p.past + q_abs) : 0x7fffffff;   // last visible key index
         uint8_t *p_row = sP + row * 128;
 
         for (int j = 0; j < n_tiles; ++j) {
             const int s = j & 1;
             const int k0 = j * kBN;
-            if (p.key_mask != nullptr) {              // stage the 128 mask bytes of this tile (double-buffered by s)
-                const int kj = k0 + tid;
-                s_kmask[s * 128 + tid] = (kj < p.Tkv) ? p.key_mask[(long)b * p.Tkv + kj] : 0;
+            if (p.key_mask != nullptr) {              // stage the mask bytes of this tile (double-buffered by s)
+                if (tid < kBN) {
+                    const int kj = k0 + tid;
+                    s_kmask[s * kBN + tid] = (kj < p.Tkv) ? p.key_mask[(long)b * p.Tkv + kj] : 0;
+                }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
             bar_wait(s_full + s, (j >> 1) & 1);
             tc_fence_after();
             const bool need_mask = (k0 + kBN - 1 > causal_limit) || (k0 + kBN > p.Tkv) || (p.key_mask != nullptr);
-            const uint32_t t_s = tmem_s0 + (uint32_t)s * 128u + lane_sel;
 
-            // pass 1: row max of the (masked) scores
+            float sc[kBN];
+            tmem_ld64(tmem_s0 + (uint32_t)s * kBN + lane_sel, sc);
             float m_tile = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < kBN; c += 32) {
-                float v[32];
-                tmem_ld32(t_s + c, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float x = v[i];
-                    if (need_mask) {
-                        const int kj = k0 + c + i;
-                        const bool ok = (kj <= causal_limit) && (kj < p.Tkv) && (p.key_mask == nullptr || s_kmask[s * 128 + c + i]);
-                        x = ok ? x : -INFINITY;
-                    }
-                    m_tile = fmaxf(m_tile, x);
+            for (int i = 0; i < kBN; ++i) {
+                if (need_mask) {
+                    const int kj = k0 + i;
+                    const bool ok = (kj <= causal_limit) && (kj < p.Tkv) && (p.key_mask == nullptr || s_kmask[s * kBN + i]);
+                    sc[i] = ok ? sc[i] : -INFINITY;
                 }
+                m_tile = fmaxf(m_tile, sc[i]);
             }
-            const float m_new = fmaxf(m_run, m_tile);
-            const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2e;
-            const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run * p.scale_log2e - m_scaled);
+            const float m_cand = fmaxf(m_ref, m_tile);
+            const bool grow = (m_cand > m_ref) && (m_ref == -INFINITY || (m_cand - m_ref) * p.scale_log2e > kRescaleThreshold);
+            const float alpha = grow ? ((m_ref == -INFINITY) ? 0.f : fast_exp2((m_ref - m_cand) * p.scale_log2e)) : 1.f;
+            if (grow) m_ref = m_cand;
+            const float m_scaled = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2e;
 
-            // the previous P V must have retired before P is overwritten and O is rescaled
+            // P = exp2(S * scale_log2e - m_ref), row sum, pack to 16 bit
+            float l_tile = 0.f;
+            uint32_t pk[kBN / 2];
+#pragma unroll
+            for (int i = 0; i < kBN; i += 2) {
+                const float e0 = fast_exp2(sc[i] * p.scale_log2e - m_scaled);       // masked: exp2(-inf) = 0
+                const float e1 = fast_exp2(sc[i + 1] * p.scale_log2e - m_scaled);
+                l_tile += e0 + e1;
+                pk[i >> 1] = pack2<T>(e0, e1);
+            }
+            l_run = l_run * alpha + l_tile;
+
+            // the previous P V must have retired before P is overwritten / O is rescaled
+            const bool any_grow = __any_sync(0xffffffffu, grow) && (j > 0);
             if (j > 0) {
                 bar_wait(o_ready, (j - 1) & 1);
                 tc_fence_after();
+            }
+            if (any_grow) {                           // warp-uniform: tcgen05.ld/st are warp-collective
 #pragma unroll 1
-                for (int c = 0; c < HD; c += 32) {   // O *= alpha (this thread's row)
+                for (int c = 0; c < HD; c += 32) {
                     float o[32];
                     tmem_ld32(tmem_o + lane_sel + c, o);
 #pragma unroll
@@ -301,40 +350,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     tmem_st32(tmem_o + lane_sel + c, o);
                 }
             }
-
-            // pass 2: P = exp2(S * scale_log2e - m), row sum, bf16 into the swizzled A-operand tile
-            float l_tile = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < kBN; c += 32) {
-                float v[32];
-                tmem_ld32(t_s + c, v);
+            // 64 keys = 128 B = 8 chunks of 16 B, chunk index XOR (row % 8): SWIZZLE_128B
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float e = exp2f(v[i] * p.scale_log2e - m_scaled);
-                    if (need_mask) {
-                        const int kj = k0 + c + i;
-                        const bool ok = (kj <= causal_limit) && (kj < p.Tkv) && (p.key_mask == nullptr || s_kmask[s * 128 + c + i]);
-                        e = ok ? e : 0.f;
-                    }
-                    v[i] = e;
-                    l_tile += e;
-                }
-                // 32 keys = 64 B = 4 chunks of 16 B; box = c / 64, chunk index within the 128-B row = (c % 64)/8 + q
-                uint8_t *box_row = p_row + (c >> 6) * BOX_BYTES;
-#pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                    const int chunk = ((c & 63) >> 3) + qd;
-                    const int phys = chunk ^ (row & 7);                       // SWIZZLE_128B
-                    uint4 w;
-                    w.x = pack2<T>(v[qd * 8 + 0], v[qd * 8 + 1]);
-                    w.y = pack2<T>(v[qd * 8 + 2], v[qd * 8 + 3]);
-                    w.z = pack2<T>(v[qd * 8 + 4], v[qd * 8 + 5]);
-                    w.w = pack2<T>(v[qd * 8 + 6], v[qd * 8 + 7]);
-                    *reinterpret_cast<uint4 *>(box_row + phys * 16) = w;
-                }
+            for (int ch = 0; ch < 8; ++ch) {
+                const int phys = ch ^ (row & 7);
+                *reinterpret_cast<uint4 *>(p_row + phys * 16) = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
             }
-            l_run = l_run * alpha + l_tile;
-            m_run = m_new;
             fence_async_smem();        // generic-proxy writes of P -> visible to the tensor core (async proxy)
             tc_fence_before();
             bar_arrive(p_full);
@@ -414,7 +435,7 @@ static int make_map(CUtensorMap *map, const void *ptr, int dtype, int B, int T, 
 
 template <typename T, int HD>
 static int launch_attn(const CUtensorMap &mq, const CUtensorMap &mk, const CUtensorMap &mv, const AttnParams &p, cudaStream_t st) {
-    constexpr size_t smem = 1024 + (size_t)(HD / 64) * 128 * 128 * 5 + 2 * 128 * 128 + 14 * 8 + 2 * 128 + 64;
+    constexpr size_t smem = (size_t)(HD / 64) * (kBM * 128 + 4 * kBN * 128) + kBM * 128 + 14 * 8 + 2 * kBN + 16;
     auto kern = attn_fwd_kernel<T, HD>;
     static bool attr_set = false;
     if (!attr_set) {
