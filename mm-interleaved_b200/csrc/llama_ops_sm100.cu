@@ -88,28 +88,32 @@ __global__ void __launch_bounds__(256) rope_qk_kernel(T *__restrict__ q, T *__re
                                                        const float *__restrict__ sin_t, const int64_t *__restrict__ pos,
                                                        long n_tok, int H, int hd, int q_stride, int k_stride, int pos_per_batch,
                                                        int T_len) {
-    // one thread per (token, head, pair i < hd/2); handles q and k
+    // one thread per (token, head, q-or-k, chunk of VEC rotation pairs): two 16-byte loads (x1 | x2 halves),
+    // two 16-byte stores; cos/sin rows are fp32 and L1/L2 resident (one row per token)
+    constexpr int VEC = 16 / (int)sizeof(T);
     const int half = hd >> 1;
-    const long total = n_tok * H * half;
+    const int chunks = half / VEC;
+    const long total = n_tok * H * 2 * chunks;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int i = (int)(idx % half);
-        const long th = idx / half;
-        const int h = (int)(th % H);
-        const long tok = th / H;
+        const int c = (int)(idx % chunks);
+        long r = idx / chunks;
+        const int which = (int)(r & 1); r >>= 1;
+        const int h = (int)(r % H);
+        const long tok = r / H;
         const long p = pos[pos_per_batch ? tok : (tok % T_len)];
-        const float c = rnd<T>(cos_t[p * hd + i]), s = rnd<T>(sin_t[p * hd + i]);   // tables cast to x.dtype (:141-144)
-        {
-            T *x = q + tok * q_stride + (size_t)h * hd;
-            const float x1 = to_op(x[i]), x2 = to_op(x[i + half]);
-            x[i] = from_op<T>(rnd<T>(x1 * c) + rnd<T>(-x2 * s));
-            x[i + half] = from_op<T>(rnd<T>(x2 * c) + rnd<T>(x1 * s));
+        T *x = (which ? k + tok * k_stride : q + tok * q_stride) + (size_t)h * hd + c * VEC;
+        float x1[VEC], x2[VEC], o1[VEC], o2[VEC];
+        Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(x), x1);
+        Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(x + half), x2);
+        const float *cp = cos_t + p * hd + c * VEC, *sp = sin_t + p * hd + c * VEC;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float cs = rnd<T>(cp[i]), sn = rnd<T>(sp[i]);          // tables cast to x.dtype (:141-144)
+            o1[i] = rnd<T>(x1[i] * cs) + rnd<T>(-x2[i] * sn);
+            o2[i] = rnd<T>(x2[i] * cs) + rnd<T>(x1[i] * sn);
         }
-        {
-            T *x = k + tok * k_stride + (size_t)h * hd;
-            const float x1 = to_op(x[i]), x2 = to_op(x[i + half]);
-            x[i] = from_op<T>(rnd<T>(x1 * c) + rnd<T>(-x2 * s));
-            x[i + half] = from_op<T>(rnd<T>(x2 * c) + rnd<T>(x1 * s));
-        }
+        *reinterpret_cast<uint4 *>(x) = Vec16<T>::pack(o1);
+        *reinterpret_cast<uint4 *>(x + half) = Vec16<T>::pack(o2);
     }
 }
 
@@ -143,7 +147,7 @@ static int launch_all(int which, const void *a, const void *b, const void *c, vo
             layernorm_kernel<T><<<(unsigned)n0, 256, 0, st>>>((const T *)a, (const T *)b, (const T *)c, (T *)d, i0, eps);
             break;
         case 2: { // rope: d=q (in place), a=k (in place, cast away const), e=cos f=sin c=pos; n0=tokens i0=H i1=hd i2=q_stride i3=k_stride i4=pos_per_batch i5=T
-            const long total = n0 * i0 * (i1 / 2);
+            const long total = n0 * i0 * 2 * ((i1 / 2) / (16 / (int)sizeof(T)));
             const int grid = (int)((total + 255) / 256 < 148L * 16 ? (total + 255) / 256 : 148L * 16);
             rope_qk_kernel<T><<<grid, 256, 0, st>>>((T *)d, (T *)const_cast<void *>(a), (const float *)e, (const float *)f,
                                                      (const int64_t *)c, n0, i0, i1, i2, i3, i4, i5);
@@ -198,6 +202,9 @@ extern "C" int mmfs_rope_qk(void *q, void *k, const float *cos_table, const floa
     MMFS_CHECK_ARG(n_tokens >= 0 && H > 0 && hd > 0 && hd % 2 == 0 && T_len > 0, "rope_qk: bad shape");
     if (n_tokens == 0) return MMFS_OK;
     MMFS_CHECK_ARG(q && k && cos_table && sin_table && position_ids, "rope_qk: null pointer argument");
+    MMFS_CHECK_ARG((hd / 2) % (16 / (int)dtype_size(dtype)) == 0 && ((uintptr_t)q | (uintptr_t)k) % 16 == 0 &&
+                   (q_stride * dtype_size(dtype)) % 16 == 0 && (k_stride * dtype_size(dtype)) % 16 == 0,
+                   "rope_qk: head_dim/2 must be a multiple of the 16-byte vector and rows 16-byte aligned");
     return dispatch(dtype, 2, k, nullptr, position_ids, q, cos_table, sin_table, n_tokens, H, hd, q_stride, k_stride,
                     pos_per_batch, T_len, 0.f, stream);
 }
