@@ -40,6 +40,10 @@ extern "C" {
 #define MMFS_MSDA_STRICT 1u /* also fetch taps whose attention weight is exactly 0 (the
                                reference multiplies them in, which only matters when
                                `value` holds inf/nan); default skips those fetches */
+#define MMFS_MSDA_W16    2u /* 16-bit element types only: round each tap weight (lerp * attention weight) to the
+                               element type and accumulate with the mixed-precision FMA (fma.rn.f32.bf16/f16,
+                               SASS FHFMA) -- fewer instructions per fetch; the reference keeps fp32 weights, so
+                               this is opt-in (error << one storage ulp of the result) */
 
 int mmfs_abi_version(void);
 const char *mmfs_last_error(void);

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("MMFS_B200_LIB", os.path.join(_HERE, "libmmfs_b200.so"
 OK, EINVAL, EUNSUPPORTED, ECUDA = 0, -1, -2, -3
 F32, F16, BF16, F64 = 0, 1, 2, 3
 MSDA_STRICT = 1
+MSDA_W16 = 2
 
 _lib = None
 

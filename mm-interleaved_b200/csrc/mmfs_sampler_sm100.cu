@@ -75,12 +75,15 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, 3) mmfs_sampler_kernel(cons
     int4 *s_lvl = s_dyn;
     float *s_scale = reinterpret_cast<float *>(s_dyn + L);
     const int scale_slots = (n_lvl + 3) / 4;  // int4 units
-    const int xs_elems = ((L * P + 3) / 4) * 4;
-    const int per_warp_bytes = kTapsPerWarp * (int)sizeof(Tap) + xs_elems * 4 + 128;
+    const int xs_elems = n_img * ((n_lvl * P + 31) / 32) * 32;
+    const int q_elems = P * 2 + n_lvl * (P + 1);              // this head's slice of a qproj row: offsets | logits
+    const int qs_elems = ((q_elems + 3) / 4) * 4;
+    const int per_warp_bytes = kTapsPerWarp * (int)sizeof(Tap) + (xs_elems + qs_elems) * 4 + 128;
     char *wbase = reinterpret_cast<char *>(s_dyn + L + scale_slots) + warp * per_warp_bytes;
     Tap *taps = reinterpret_cast<Tap *>(wbase);
     float *xs = reinterpret_cast<float *>(wbase + kTapsPerWarp * sizeof(Tap));
-    int *s_vis = reinterpret_cast<int *>(wbase + kTapsPerWarp * sizeof(Tap) + xs_elems * 4);
+    float *qs = xs + xs_elems;                                // [P*2 offsets | n_lvl*(P+1) logits] of the current row, fp32
+    int *s_vis = reinterpret_cast<int *>(wbase + kTapsPerWarp * sizeof(Tap) + (xs_elems + qs_elems) * 4);
 
     for (int l = threadIdx.x; l < L; l += blockDim.x)
         s_lvl[l] = make_int4((int)a.shapes[2 * l], (int)a.shapes[2 * l + 1], (int)a.starts[l], 0);
@@ -93,28 +96,56 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, 3) mmfs_sampler_kernel(cons
     const int C = M * P * 2 + M * n_lvl * (P + 1);
     const long long row_bytes = (long long)M * D * (int)sizeof(T);
     const bool strict = a.flags & MMFS_MSDA_STRICT;
+    const bool w16 = a.flags & MMFS_MSDA_W16;
     const int slot = lane / LPR;
     const float nullv = round_to<T>(a.null_logit);
-    const int per_img = n_lvl * P;
+    const int per_img = n_lvl * P;                            // sampling items of one image
+    const int img_passes = (per_img + 31) / 32;               // 1 for every shipped configuration (24 or 32 items)
+    const int l_lane = lane / P, p_lane = lane - l_lane * P;  // (level, point) of this lane's item in pass 0
 
     RowWalk walk;
     walk.itiles = (int)a.ntiles; walk.igrid = (int)gridDim.x; walk.qtiles = a.qtiles; walk.M = M; walk.Lq = Lq;
     walk.rows_per_warp = a.rows_per_warp; walk.warp = warp;
 
-    for (RowCursor cur = walk.first(a.ctas_per_sm, a.nsm, a.swizzle); cur.ok; cur = walk.next(cur)) {
+    // Everything a row needs from HBM -- its relpos bytes and its head's slice of the qproj row -- is
+    // fetched one row AHEAD into registers, so a row's critical path only sees shared memory, the
+    // L1-resident relpos table and the gathers.
+    constexpr int kQPre = 4;                                  // supports slices of up to 128 elements
+    if (q_elems > 32 * kQPre) { asm volatile("trap;"); }
+    const int q_loads = (q_elems + 31) / 32;
+    float pre_q[kQPre];
+    int pre_r = 0;
+    auto prefetch = [&](const RowCursor &c) {
+        const T *qp = qproj + ((size_t)c.b * Lq + c.q) * C;
+        const int ob = c.m * P * 2, ab = M * P * 2 + c.m * n_lvl * (P + 1);
+#pragma unroll
+        for (int t = 0; t < kQPre; ++t) {
+            const int e = lane + 32 * t;
+            pre_q[t] = 0.f;
+            if (t < q_loads && e < q_elems) pre_q[t] = to_op(qp[e < P * 2 ? ob + e : ab + (e - P * 2)]);
+        }
+        pre_r = 0;
+        if (lane < n_img) pre_r = a.relpos[((size_t)c.b * n_img + lane) * a.Lq_r + (a.Lq_r == 1 ? 0 : c.q)];
+    };
+    RowCursor cur = walk.first(a.ctas_per_sm, a.nsm, a.swizzle);
+    if (cur.ok) prefetch(cur);
+
+    while (cur.ok) {
         const int b = cur.b, m = cur.m, q = cur.q;
-        const size_t bq = (size_t)b * Lq + q;
-        const size_t qm = bq * M + m;
-        const T *qp = qproj + bq * C;
+        const size_t qm = ((size_t)b * Lq + q) * M + m;
         const int off_base = m * P * 2, att_base = M * P * 2 + m * n_lvl * (P + 1);
+        __syncwarp();                                         // previous row done with qs / xs / s_vis
+#pragma unroll
+        for (int t = 0; t < kQPre; ++t)
+            if (t < q_loads && lane + 32 * t < q_elems) qs[lane + 32 * t] = pre_q[t];
+        const int r_mine = pre_r;
+        const RowCursor nxt = walk.next(cur);
+        if (nxt.ok) prefetch(nxt);                            // loads for the next row are now in flight
 
         // ---- visible images of this token (mask row; last row if the mask is shorter) ---------
-        int r_mine = 0;
-        if (lane < n_img) r_mine = a.relpos[((size_t)b * n_img + lane) * a.Lq_r + (a.Lq_r == 1 ? 0 : q)];
         const unsigned vis = __ballot_sync(0xffffffffu, r_mine != 0);
         const int nvis = __popc(vis);
-        __syncwarp();
-        // list of images to walk: the visible ones (EMIT: all, masked ones flagged by bit 31)
+        // list of images to walk: the visible ones (EMIT: all, masked ones flagged by bit 30)
         if (EMIT) {
             if (lane < n_img) s_vis[lane] = lane | (r_mine << 8) | (r_mine == 0 ? (1 << 30) : 0);
         } else if (r_mine != 0) {
@@ -122,31 +153,28 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, 3) mmfs_sampler_kernel(cons
         }
         __syncwarp();
         const int nlist = EMIT ? n_img : nvis;
-        const int items = nlist * per_img;
 
         // ---- pass A: logits of the listed images -> xs[], softmax statistics ------------------
+        // one pass per (image, chunk of 32 items): lane = item = (level, point) of that image
         float lmax = nullv;
-        for (int k0 = 0; k0 < items; k0 += 32) {
-            const int k = k0 + lane;
-            if (k < items) {
-                const int vi = k / per_img, rem = k - vi * per_img;
-                const int l = rem / P, p = rem - l * P;
-                const int e = s_vis[vi];
-                const int r = (e >> 8) & 0xff;
-                const int col = att_base + l * (P + 1) + p;
-                float x = round_to<T>(to_op(qp[col]) + to_op(rtable[(size_t)r * C + col]));
-                if (e & (1 << 30)) x = -INFINITY;   // EMIT only: masked image -> weight exactly 0
-                xs[k] = x;
-                lmax = fmaxf(lmax, x);
+        for (int vi = 0; vi < nlist; ++vi) {
+            const int e = s_vis[vi];
+            const T *rt = rtable + (size_t)((e >> 8) & 0xff) * C + att_base;
+            for (int c0 = 0; c0 < img_passes; ++c0) {
+                const int it = c0 * 32 + lane;
+                if (it < per_img) {
+                    const int l = c0 == 0 ? l_lane : it / P, pp = c0 == 0 ? p_lane : it - (it / P) * P;
+                    float x = round_to<T>(qs[P * 2 + l * (P + 1) + pp] + to_op(rt[l * (P + 1) + pp]));
+                    if (e & (1 << 30)) x = -INFINITY;   // EMIT only: masked image -> weight exactly 0
+                    xs[(vi * img_passes + c0) * 32 + lane] = x;
+                    lmax = fmaxf(lmax, x);
+                }
             }
         }
         lmax = warp_max(lmax);
-        __syncwarp();
         float lsum = 0.f;
-        for (int k0 = 0; k0 < items; k0 += 32) {
-            const int k = k0 + lane;
-            if (k < items) lsum += expf(xs[k] - lmax);
-        }
+        for (int vi = 0; vi < nlist * img_passes; ++vi)
+            if ((vi % img_passes) * 32 + lane < per_img) lsum += expf(xs[vi * 32 + lane] - lmax);
         const float e_null = expf(nullv - lmax);
         const float denom = warp_sum(lsum) + (float)L * e_null;   // one null slot per level, mmfs.py:225
         if (a.null_mass != nullptr && lane == 0)
@@ -157,6 +185,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, 3) mmfs_sampler_kernel(cons
 #pragma unroll
             for (int k = 0; k < VEC; ++k) zero[k] = 0.f;
             if (lane < LPR) stg_v4(static_cast<T *>(a.out) + qm * D + lane * VEC, Vec16<T>::pack(zero));
+            cur = nxt;
             continue;
         }
 
@@ -167,64 +196,67 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, 3) mmfs_sampler_kernel(cons
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
 
-        // ---- pass B: weights, sampling locations, taps, gather --------------------------------
-        for (int k0 = 0; k0 < items; k0 += 32) {
-            const int k = k0 + lane;
-            bool live = false;
-            PointGeom<float> g;
-            g.in_range = false; g.h_low = g.w_low = 0; g.lh = g.lw = 0.f;
-            float aw = 0.f;
-            int4 lv = make_int4(1, 1, 0, 0);
-            if (k < items) {
-                const int vi = k / per_img, rem = k - vi * per_img;
-                const int l = rem / P, p = rem - l * P;
-                const int e = s_vis[vi];
-                const int img = e & 0xff, r = (e >> 8) & 0xff;
-                const int gl = img * n_lvl + l;                       // global level index (n l), mmfs.py:198
-                aw = round_to<T>(__fdiv_rn(expf(xs[k] - lmax), denom));
-                if (EMIT || strict || aw != 0.f) {
-                    lv = s_lvl[gl];
-                    const int col = off_base + p * 2;
-                    const float ox = round_to<T>(to_op(qp[col]) + to_op(rtable[(size_t)r * C + col]));
-                    const float oy = round_to<T>(to_op(qp[col + 1]) + to_op(rtable[(size_t)r * C + col + 1]));
-                    const float sc = s_scale[l];
-                    // off * scale_ratio (mmfs.py:194-195), / (W, H) (mmfs.py:248-249): each a tensor op in
-                    // the storage type in the reference, hence the intermediate roundings
-                    const float tx = round_to<T>(__fdiv_rn(round_to<T>(__fmul_rn(ox, sc)), (float)lv.y));
-                    const float ty = round_to<T>(__fdiv_rn(round_to<T>(__fmul_rn(oy, sc)), (float)lv.x));
-                    const float *rp = a.refpts + ((((size_t)(a.Nr == 1 ? 0 : b) * Lq + q) * a.Lr) + (a.Lr == 1 ? 0 : gl)) * 2;
-                    const float x = round_to<T>(__fadd_rn(rp[0], tx));   // fp32 ref + offset, cast to value dtype (mmfs.py:265)
-                    const float y = round_to<T>(__fadd_rn(rp[1], ty));
-                    if (EMIT) {
-                        const size_t o = (qm * L + gl) * P + p;
-                        static_cast<T *>(a.loc_out)[2 * o] = from_op<T>(x);
-                        static_cast<T *>(a.loc_out)[2 * o + 1] = from_op<T>(y);
-                        static_cast<T *>(a.attn_out)[o] = from_op<T>(aw);
-                    } else {
-                        g = point_geom(x, y, lv.x, lv.y);
-                        live = g.in_range;
+        // ---- pass B: weights, sampling locations, taps, gather (one pass per image chunk) ------
+        for (int vi = 0; vi < nlist; ++vi) {
+            const int e = s_vis[vi];
+            const int img = e & 0xff;
+            const T *rt = rtable + (size_t)((e >> 8) & 0xff) * C + off_base;
+            for (int c0 = 0; c0 < img_passes; ++c0) {
+                const int it = c0 * 32 + lane;
+                bool live = false;
+                PointGeom<float> g;
+                g.in_range = false; g.h_low = g.w_low = 0; g.lh = g.lw = 0.f;
+                float aw = 0.f;
+                int4 lv = make_int4(1, 1, 0, 0);
+                if (it < per_img) {
+                    const int l = c0 == 0 ? l_lane : it / P, pp = c0 == 0 ? p_lane : it - (it / P) * P;
+                    const int gl = img * n_lvl + l;                   // global level index (n l), mmfs.py:198
+                    aw = round_to<T>(__fdiv_rn(expf(xs[(vi * img_passes + c0) * 32 + lane] - lmax), denom));
+                    if (EMIT || strict || aw != 0.f) {
+                        lv = s_lvl[gl];
+                        const float ox = round_to<T>(qs[pp * 2] + to_op(rt[pp * 2]));
+                        const float oy = round_to<T>(qs[pp * 2 + 1] + to_op(rt[pp * 2 + 1]));
+                        const float sc = s_scale[l];
+                        // off * scale_ratio (mmfs.py:194-195), / (W, H) (mmfs.py:248-249): each a tensor op in
+                        // the storage type in the reference, hence the intermediate roundings
+                        const float tx = round_to<T>(__fdiv_rn(round_to<T>(__fmul_rn(ox, sc)), (float)lv.y));
+                        const float ty = round_to<T>(__fdiv_rn(round_to<T>(__fmul_rn(oy, sc)), (float)lv.x));
+                        const float *rp = a.refpts + ((((size_t)(a.Nr == 1 ? 0 : b) * Lq + q) * a.Lr) + (a.Lr == 1 ? 0 : gl)) * 2;
+                        const float x = round_to<T>(__fadd_rn(rp[0], tx));   // fp32 ref + offset, cast to value dtype (mmfs.py:265)
+                        const float y = round_to<T>(__fadd_rn(rp[1], ty));
+                        if (EMIT) {
+                            const size_t o = (qm * L + gl) * P + pp;
+                            static_cast<T *>(a.loc_out)[2 * o] = from_op<T>(x);
+                            static_cast<T *>(a.loc_out)[2 * o + 1] = from_op<T>(y);
+                            static_cast<T *>(a.attn_out)[o] = from_op<T>(aw);
+                        } else {
+                            g = point_geom(x, y, lv.x, lv.y);
+                            live = g.in_range;
+                        }
                     }
                 }
+                if (EMIT) continue;
+                const unsigned livemask = __ballot_sync(0xffffffffu, live);
+                if (livemask == 0u) continue;
+                __syncwarp();
+                emit_taps(taps, lane, live, g, aw, lv.x, lv.y, lv.z, row_bytes, zero_off);
+                __syncwarp();
+                gather_pass_any<T, D>(taps, livemask, vbase, slot, acc, w16);
             }
-            if (EMIT) continue;
-            const unsigned livemask = __ballot_sync(0xffffffffu, live);
-            if (livemask == 0u) continue;
-            __syncwarp();
-            emit_taps(taps, lane, live, g, aw, lv.x, lv.y, lv.z, row_bytes, zero_off);
-            __syncwarp();
-            gather_pass<T, D>(taps, livemask, vbase, slot, acc);
         }
         if (!EMIT) store_row<T, D>(acc, static_cast<T *>(a.out) + qm * D, lane);
-        __syncwarp();   // xs / s_vis are rewritten by the next row
+        cur = nxt;
     }
 }
 
 template <typename T, int D, bool EMIT>
 static int launch_sampler(SamplerArgs a, int N, cudaStream_t st) {
     const int L = a.n_img * a.n_lvl;
-    const int xs_elems = ((L * a.P + 3) / 4) * 4;
+    const int xs_elems = a.n_img * ((a.n_lvl * a.P + 31) / 32) * 32;
+    const int qs_elems = ((a.P * 2 + a.n_lvl * (a.P + 1) + 3) / 4) * 4;
+    if (a.P * 2 + a.n_lvl * (a.P + 1) > 128) { set_error("mmfs_sampler: P*2 + n_lvl*(P+1) > 128 unsupported"); return MMFS_EUNSUPPORTED; }
     const size_t smem = (size_t)(L + (a.n_lvl + 3) / 4) * sizeof(int4) +
-                        (size_t)kWarpsPerCta * (kTapsPerWarp * sizeof(Tap) + (size_t)xs_elems * 4 + 128);
+                        (size_t)kWarpsPerCta * (kTapsPerWarp * sizeof(Tap) + (size_t)(xs_elems + qs_elems) * 4 + 128);
     if (smem > 200 * 1024) { set_error("mmfs_sampler: n_img*n_lvl*P = %d too large", L * a.P); return MMFS_EUNSUPPORTED; }
     auto kern = mmfs_sampler_kernel<T, D, EMIT>;
     static thread_local size_t smem_set = 0;

@@ -65,6 +65,7 @@ msda_fwd_rows_kernel(const T *__restrict__ value, const int64_t *__restrict__ sh
     const int LP = L * P;
     const long long row_bytes = (long long)M * D * (int)sizeof(T);
     const bool strict = flags & MMFS_MSDA_STRICT;
+    const bool w16 = flags & MMFS_MSDA_W16;
     const int slot = lane / LPR;
     const uint32_t loc_bytes = (uint32_t)(2 * LP * (int)sizeof(T)), att_bytes = (uint32_t)(LP * (int)sizeof(T));
 
@@ -136,7 +137,7 @@ msda_fwd_rows_kernel(const T *__restrict__ value, const int64_t *__restrict__ sh
             emit_taps(taps, lane, live, g, a, lv.x, lv.y, lv.z, row_bytes, zero_off);
             __syncwarp();
             // ---- phase 2 -------------------------------------------------------------------
-            gather_pass<T, D>(taps, livemask, vbase, slot, acc);
+            gather_pass_any<T, D>(taps, livemask, vbase, slot, acc, w16);
         }
 
         store_row<T, D>(acc, out + (((size_t)b * Lq + q) * M + m) * D, lane);
@@ -156,6 +157,7 @@ msda_fwd_generic_kernel(const T *__restrict__ value, const int64_t *__restrict__
                         long total, int S, int M, int D, int L, int Lq, int P, unsigned flags) {
     using OP = typename OpMath<T>::type;
     const bool strict = flags & MMFS_MSDA_STRICT;
+    const bool w16 = flags & MMFS_MSDA_W16;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int c = (int)(idx % D);
         const long qm = idx / D;

@@ -174,6 +174,69 @@ __device__ __forceinline__ void gather_pass(const Tap *taps, unsigned livemask, 
     }
 }
 
+// Mixed-precision FMA of sm_100 (SASS FHFMA): d = a(16-bit, half selected in the register) * b(16-bit) + c(fp32).
+// It consumes the packed value register directly -- no unpack -- at the price of a 16-bit weight.
+template <typename T> struct MixFma;
+template <> struct MixFma<__nv_bfloat16> {
+    __device__ __forceinline__ static void fma(float &acc, uint16_t v, uint16_t w) {
+        asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(acc) : "h"(v), "h"(w));
+    }
+    __device__ __forceinline__ static uint16_t cvt(float w) { __nv_bfloat16 t = __float2bfloat16_rn(w); return *reinterpret_cast<uint16_t *>(&t); }
+};
+template <> struct MixFma<__half> {
+    __device__ __forceinline__ static void fma(float &acc, uint16_t v, uint16_t w) {
+        asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc) : "h"(v), "h"(w));
+    }
+    __device__ __forceinline__ static uint16_t cvt(float w) { __half t = __float2half_rn(w); return *reinterpret_cast<uint16_t *>(&t); }
+};
+
+// gather_pass with 16-bit tap weights (MMFS_MSDA_W16): 8 FHFMA per 16-byte fetch instead of 8 unpack + 4 FFMA2
+template <typename T, int D>
+__device__ __forceinline__ void gather_pass_w16(const Tap *taps, unsigned livemask, const char *vbase, int slot,
+                                                float (&acc)[16 / sizeof(T)]) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int LPR = D / VEC;
+    constexpr int RPI = 32 / LPR;
+    constexpr int NIT = 128 / RPI;
+    constexpr int G = NIT < 8 ? NIT : 8;
+    constexpr int PPG = (G * RPI) / 4;
+    static_assert(VEC == 8, "16-bit element types only");
+#pragma unroll 1
+    for (int g0 = 0; g0 < NIT; g0 += G) {
+        const unsigned pm = (PPG >= 32) ? livemask : ((livemask >> ((g0 * RPI) / 4)) & ((1u << PPG) - 1u));
+        if (pm == 0u) continue;
+        Tap t[G];
+        uint4 v[G];
+#pragma unroll
+        for (int it = 0; it < G; ++it) {
+            const int tix = (g0 + it) * RPI + slot;
+            *reinterpret_cast<uint4 *>(&t[it]) =
+                *reinterpret_cast<const uint4 *>(&taps[(tix & 3) * kTapStride + (tix >> 2)]);
+        }
+#pragma unroll
+        for (int it = 0; it < G; ++it) v[it] = ldg_nc_v4(vbase + t[it].off);
+#pragma unroll
+        for (int it = 0; it < G; ++it) {
+            const uint16_t w = MixFma<T>::cvt(t[it].w0);
+            const uint32_t r[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                MixFma<T>::fma(acc[2 * k], (uint16_t)(r[k] & 0xffffu), w);
+                MixFma<T>::fma(acc[2 * k + 1], (uint16_t)(r[k] >> 16), w);
+            }
+        }
+    }
+}
+// dispatch: 16-bit weights only for 16-bit element types and only on request
+template <typename T, int D>
+__device__ __forceinline__ void gather_pass_any(const Tap *taps, unsigned livemask, const char *vbase, int slot,
+                                                float (&acc)[16 / sizeof(T)], bool w16) {
+    if constexpr (sizeof(T) == 2) {
+        if (w16) { gather_pass_w16<T, D>(taps, livemask, vbase, slot, acc); return; }
+    }
+    gather_pass<T, D>(taps, livemask, vbase, slot, acc);
+}
+
 // epilogue: sum the RPI slots, one rounding, 16-byte stores
 template <typename T, int D>
 __device__ __forceinline__ void store_row(float (&acc)[16 / sizeof(T)], T *out_row, int lane) {
@@ -213,8 +276,8 @@ struct RowWalk {
         return c;
     }
     __device__ __forceinline__ RowCursor next(RowCursor c) const {
-        if (++c.r == rows_per_warp) { c.r = 0; c.tile += igrid; }
-        settle(c);
+        if (++c.r == rows_per_warp) { c.r = 0; c.tile += igrid; settle(c); return c; }
+        if (++c.q >= Lq) { c.r = 0; c.tile += igrid; settle(c); }   // same tile, next query: no divisions
         return c;
     }
 };

@@ -27,7 +27,7 @@ def _common(shapes, starts, qproj, rtable, relpos, refpts, scale_ratios, M, n_lv
 
 
 def mmfs_sampler_forward(value, shapes, starts, qproj, rtable, relpos, refpts, scale_ratios,
-                         n_levels: int, n_points: int, want_null_mass: bool = False, strict: bool = False):
+                         n_levels: int, n_points: int, want_null_mass: bool = False, strict: bool = False, w16: bool = False):
     """Fused relpos lookup + mask + null-slot softmax + location arithmetic + deformable gather.
     Returns the sampled features (N, Lq, M*D) [and the null mass (N, Lq, M) fp32]."""
     _require(value.is_cuda and value.is_contiguous() and value.dim() == 4, "value must be contiguous CUDA (N,S,M,D)")
@@ -44,7 +44,7 @@ def mmfs_sampler_forward(value, shapes, starts, qproj, rtable, relpos, refpts, s
             relpos.data_ptr(), refpts.data_ptr(), scale_ratios.data_ptr(), out.data_ptr(),
             null_mass.data_ptr() if want_null_mass else None,
             N, S, M, D, n_img, n_levels, Lq, n_points, relpos.shape[2], refpts.shape[0], refpts.shape[2],
-            rtable.shape[0], _DTYPE_CODE[value.dtype], _lib.MSDA_STRICT if strict else 0,
+            rtable.shape[0], _DTYPE_CODE[value.dtype], (_lib.MSDA_STRICT if strict else 0) | (_lib.MSDA_W16 if w16 else 0),
             torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "mmfs_sampler_forward")
     return (out, null_mass) if want_null_mass else out
