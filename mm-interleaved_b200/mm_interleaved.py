@@ -116,3 +116,41 @@ class InterleavedForward(nn.Module):
         out = self.mm_decoder(inputs_embeds=mm_embeds, attention_mask=attention_mask, vision_hidden_states=feats,
                               cross_attention_mask=cross, use_cache=False, return_dict=True)
         return self.text_decoder(out.last_hidden_state)
+
+    @torch.no_grad()
+    def generate_texts(self, text_ids, visual_output, num_image_per_seq, max_num_image: int, attention_mask=None,
+                       max_new_tokens: int = 30, eos_token_id: Optional[int] = 2, pad_token_id: int = 0):
+        """Greedy text continuation over the interleaved context -- the deterministic setting (num_beams=1,
+        do_sample=False) of ``MMInterleaved.generate_texts`` (mm_interleaved.py:598-664), which drives HF ``generate``
+        through ``CascadeLlamaForCausalLMWrapper`` (models/utils/causal_lm_cascade.py:91-204): prefill on
+        ``inputs_embeds`` with the image features, then one token per step over the KV cache, the last row of the
+        cross-attention mask serving every new token (mmfs.py:161-162), ``position_ids = cumsum(mask) - 1``
+        (causal_lm_cascade.py:179-185).  Batches are expected left-padded (collator.py:337).  Returns (B, n_new) ids."""
+        B, L = text_ids.shape
+        if attention_mask is None:
+            attention_mask = torch.ones((B, L), dtype=torch.long, device=text_ids.device)
+        mm_embeds, cross, feats = self.prepare(text_ids, visual_output, num_image_per_seq, max_num_image)
+        position_ids = (attention_mask.long().cumsum(-1) - 1).clamp(min=0)
+        out = self.mm_decoder(inputs_embeds=mm_embeds, attention_mask=attention_mask, position_ids=position_ids,
+                              vision_hidden_states=feats, cross_attention_mask=cross, use_cache=True, return_dict=True)
+        past = out.past_key_values
+        logits = self.text_decoder(out.last_hidden_state[:, -1:])
+        new_ids = []
+        finished = torch.zeros((B,), dtype=torch.bool, device=text_ids.device)
+        mask = attention_mask
+        last_cross = cross[:, -1:, :]
+        pos = position_ids[:, -1:]
+        for _ in range(max_new_tokens):
+            nxt = logits[:, -1].argmax(-1)
+            if eos_token_id is not None:
+                nxt = torch.where(finished, torch.full_like(nxt, pad_token_id), nxt)
+                finished = finished | (nxt == eos_token_id)
+            new_ids.append(nxt)
+            mask = torch.cat([mask, torch.ones((B, 1), dtype=mask.dtype, device=mask.device)], dim=1)
+            pos = pos + 1
+            step = self.mm_decoder(inputs_embeds=self.mm_decoder.embed_tokens(nxt[:, None]), attention_mask=mask,
+                                   position_ids=pos, past_key_values=past, vision_hidden_states=feats,
+                                   cross_attention_mask=last_cross, use_cache=True, return_dict=True)
+            past = step.past_key_values
+            logits = self.text_decoder(step.last_hidden_state)
+        return torch.stack(new_ids, dim=1)

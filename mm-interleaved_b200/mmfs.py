@@ -122,7 +122,9 @@ class MMFS(nn.Module):
         return value
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
-                input_padding_mask=None, attention_mask=None):
+                input_padding_mask=None, attention_mask=None, output_weight=None, output_bias=None):
+        """Reference signature (mmfs.py:120-129).  ``output_weight`` / ``output_bias`` (extension) replace
+        ``output_proj`` for callers that fold a following linear map into it (MMFSBlock's 1x1 conv)."""
         N, Len_q, _ = query.shape
         _, n_images, hw, _ = input_flatten.shape
         assert attention_mask is not None and attention_mask.ndim in (2, 3)
@@ -164,6 +166,8 @@ class MMFS(nn.Module):
         if need_null:   # ignore-token term, mmfs.py:236-241 (a frozen zeros parameter unless a checkpoint sets it)
             ign = self.ignore_token.view(1, 1, self.n_heads, -1).to(sampled.dtype)
             sampled = sampled + (ign * null_mass.unsqueeze(-1).to(sampled.dtype)).reshape(N, Len_q, -1)
+        if output_weight is not None:
+            return F.linear(sampled, output_weight, output_bias)
         return self.output_proj(sampled)
 
     _ignore_nonzero = None   # cache of (key, "ignore_token has non-zero entries")

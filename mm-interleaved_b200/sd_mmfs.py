@@ -1,0 +1,166 @@
+"""``MMFSBlock`` / ``MMFSNet`` -- the MMFS conditioning branch of the SD-2.1 UNet, B200-native.
+
+Mirrors ``mm_interleaved/models/decoders/sd_mmfs.py`` (MMFSBlock :44-145, MMFSNet :154-272): same
+constructor arguments, parameter names (``mmfs_down_blocks.N.{query_norm,feat_norm,mmfs.*,pos_embed,conv}``,
+``mmfs_mid_block.*``) and ``forward(sample, down_block_res_samples, mmfs_features, mmfs_mask)`` signature
+(:230-236), so the patched UNet forward (utils/monkey_patch/sd_unet_forward_monkey_patch.py:316-326) can call it
+unchanged.  Built for the denoise loop:
+
+* ``LayerNorm(ms_feat)`` and ``value_proj`` run ONCE per conditioning tensor and are reused by every block call
+  of every denoise step (the reference recomputes them 13 x steps x 2 times);
+* the zero-initialised 1x1 ``conv`` after MMFS is folded into ``output_proj`` (one GEMM instead of GEMM + conv);
+* the per-pixel reference grid and the resized sin-cos position embedding are cached per query size;
+* sampling runs in the fused MMFS kernel (pixel-grid reference points, 2-D image mask).
+"""
+from __future__ import annotations
+
+import math
+from functools import partial
+from typing import List
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from .mmfs import MMFS
+
+
+def sincos_pos_embed_2d(embed_dim: int, grid_size: int) -> torch.Tensor:
+    """(grid_size^2, embed_dim) 2-D sine-cosine embedding: first half encodes the row index, second half the column
+    index, each as [sin | cos] over 1/10000^(2i/d) frequencies (utils/pos_embed.py:45-95; float64 einsum like numpy)."""
+    assert embed_dim % 4 == 0
+    quarter = embed_dim // 4
+    omega = 1.0 / 10000 ** (np.arange(quarter, dtype=np.float32) / np.float32(quarter))
+    rows, cols = np.meshgrid(np.arange(grid_size, dtype=np.float32), np.arange(grid_size, dtype=np.float32), indexing="ij")
+
+    def enc(pos):
+        out = np.einsum("m,d->md", pos.reshape(-1), omega)
+        return np.concatenate([np.sin(out), np.cos(out)], axis=1)
+
+    return torch.from_numpy(np.concatenate([enc(rows), enc(cols)], axis=1)).float()
+
+
+def resize_abs_pos(abs_pos: torch.Tensor, tgt_len: int) -> torch.Tensor:
+    """``get_abs_pos`` (utils/pos_embed.py:16-40) for embeddings without a cls token: bicubic resize of the square grid."""
+    src = int(math.sqrt(abs_pos.shape[0]))
+    tgt = int(math.sqrt(tgt_len))
+    if src == tgt:
+        return abs_pos
+    x = abs_pos.float().reshape(1, src, src, -1).permute(0, 3, 1, 2)
+    x = F.interpolate(x, size=(tgt, tgt), mode="bicubic", align_corners=False)
+    return x.permute(0, 2, 3, 1).flatten(0, 2).to(abs_pos.dtype)
+
+
+def pixel_reference_points(h: int, w: int, device) -> torch.Tensor:
+    """(1, h*w, 1, 2) pixel-centre grid x=(col+.5)/w, y=(row+.5)/h (sd_mmfs.py:15-28)."""
+    ys = (torch.arange(h, device=device, dtype=torch.float32) + 0.5) / h
+    xs = (torch.arange(w, device=device, dtype=torch.float32) + 0.5) / w
+    gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+    return torch.stack((gx.reshape(-1), gy.reshape(-1)), -1)[None, :, None, :].contiguous()
+
+
+class MMFSBlock(nn.Module):
+    def __init__(self, attn_dim=1024, query_dim=320, feat_dim=1024, num_heads=16, n_points=8, n_levels=1,
+                 deform_ratio=1.0, norm_layer=partial(nn.LayerNorm, eps=1e-6), gradient_checkpointing=False,
+                 grid_size=64, offset_init_magnitude=1, max_num_image_per_seq=10, spatial_shapes=[16],
+                 base_spatial_shape=8, layer_idx=0):
+        super().__init__()
+        self.query_norm = norm_layer(query_dim)
+        self.feat_norm = norm_layer(feat_dim)
+        self.mmfs = MMFS(d_model=attn_dim, d_query=query_dim, d_value=feat_dim, d_out=query_dim, n_levels=n_levels,
+                         n_heads=num_heads, n_points=n_points, ratio=deform_ratio,
+                         offset_init_magnitude=offset_init_magnitude, spatial_shapes=spatial_shapes,
+                         base_spatial_shape=base_spatial_shape, max_num_image_per_seq=max_num_image_per_seq,
+                         layer_idx=layer_idx)
+        self.pos_embed = nn.Parameter(sincos_pos_embed_2d(query_dim, grid_size), requires_grad=False)
+        self.conv = nn.Conv2d(query_dim, query_dim, kernel_size=1, stride=1)
+        nn.init.zeros_(self.conv.weight)       # zero_module (:148-151)
+        nn.init.zeros_(self.conv.bias)
+        self._cache = {}
+        self._feat_cache = None
+        self._fused_out = None
+
+    def _reset_parameters(self):
+        self.mmfs._reset_parameters()
+
+    def _geometry(self, device, dtype, h, w, n_images, spatial_shapes):
+        key = (device, dtype, h, w, n_images, tuple(spatial_shapes), self.pos_embed._version)
+        if key not in self._cache:
+            ss = torch.tensor(list(spatial_shapes) * n_images, dtype=torch.long)
+            starts = torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1]))
+            pos = resize_abs_pos(self.pos_embed.detach(), h * w).to(device=device, dtype=dtype)
+            self._cache[key] = (pixel_reference_points(h, w, device), ss.to(device), starts.to(device), pos)
+        return self._cache[key]
+
+    def _out_conv_fused(self):
+        """conv1x1(output_proj(x)) = (Wc Wo) x + (Wc bo + bc): one GEMM."""
+        ps = (self.mmfs.output_proj.weight, self.mmfs.output_proj.bias, self.conv.weight, self.conv.bias)
+        key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
+        if self._fused_out is None or self._fused_out[0] != key:
+            with torch.no_grad():
+                wc = self.conv.weight.view(self.conv.weight.shape[0], -1).float()
+                w = (wc @ ps[0].float()).to(ps[0].dtype).contiguous()
+                b = (wc @ ps[1].float() + ps[3].float()).to(ps[0].dtype).contiguous()
+            self._fused_out = (key, w, b)
+        return self._fused_out[1], self._fused_out[2]
+
+    def normalised_features(self, ms_feat):
+        key = (ms_feat.data_ptr(), tuple(ms_feat.shape), ms_feat._version, self.feat_norm.weight._version)
+        if self._feat_cache is None or self._feat_cache[0] != key:
+            self._feat_cache = (key, ops.layernorm(ms_feat.contiguous(), self.feat_norm.weight, self.feat_norm.bias,
+                                                   self.feat_norm.eps))
+        return self._feat_cache[1]
+
+    def forward(self, sample, ms_feat, ms_feat_mask, spatial_shapes):
+        """sample (B, C_q, H, W); ms_feat (B, N, sum(H_l*W_l), C_v); ms_feat_mask (B, N); returns the residual (B, C_q, H, W)."""
+        B, C, H, W = sample.shape
+        n_images = ms_feat_mask.shape[-1]
+        ref, ss, starts, pos = self._geometry(sample.device, sample.dtype, H, W, n_images, spatial_shapes)
+        query = sample.flatten(2).transpose(1, 2).contiguous()                       # b c h w -> b (h w) c
+        query = ops.layernorm(query, self.query_norm.weight, self.query_norm.bias, self.query_norm.eps) + pos
+        feat = self.normalised_features(ms_feat)
+        # MMFS up to the sampled features, then output_proj and the 1x1 conv as one fused linear
+        w, b = self._out_conv_fused()
+        out = self.mmfs(query, ref, feat, ss, starts, input_padding_mask=None, attention_mask=ms_feat_mask,
+                        output_weight=w, output_bias=b)
+        return out.transpose(1, 2).reshape(B, C, H, W)
+
+
+class MMFSNet(nn.Module):
+    def __init__(self, input_channel, block_out_channels, layers_per_block, downsample_factor=1, n_levels=4, n_points=8,
+                 gradient_checkpointing=True, spatial_shapes=[64, 32, 16, 8]) -> None:
+        super().__init__()
+        self.downsample_factor = downsample_factor
+        sd_shapes = [s // downsample_factor for s in spatial_shapes]
+
+        def block(query_dim, shape_idx, layer_idx):
+            return MMFSBlock(query_dim=query_dim, feat_dim=input_channel, n_points=n_points, n_levels=n_levels,
+                             grid_size=64 // downsample_factor, spatial_shapes=spatial_shapes,
+                             base_spatial_shape=sd_shapes[shape_idx], layer_idx=layer_idx)
+
+        blocks = []
+        blocks.append(block(block_out_channels[0], len(blocks) // 3, len(blocks)))          # conv_in skip (:190-197)
+        for i, ch in enumerate(block_out_channels):
+            for _ in range(layers_per_block):
+                blocks.append(block(ch, len(blocks) // 3, len(blocks)))
+            if i != len(block_out_channels) - 1:
+                blocks.append(block(ch, len(blocks) // 3, len(blocks)))                    # downsampler skip
+        self.mmfs_down_blocks = nn.ModuleList(blocks)
+        self.mmfs_mid_block = block(block_out_channels[-1], -1, len(blocks))
+
+    def forward(self, sample: torch.Tensor, down_block_res_samples: List[torch.Tensor],
+                mmfs_features: List[torch.Tensor], mmfs_mask: torch.Tensor):
+        assert len(down_block_res_samples) == len(self.mmfs_down_blocks)
+        spatial_shapes = [(int(f.shape[-2]), int(f.shape[-1])) for f in mmfs_features]
+        key = tuple((f.data_ptr(), f._version, tuple(f.shape)) for f in mmfs_features)
+        if getattr(self, "_packed", None) is None or self._packed[0] != key:   # constant across denoise steps
+            feats = torch.cat([f.flatten(3).transpose(2, 3) for f in mmfs_features], dim=2).contiguous()   # b n (h w) c
+            self._packed = (key, feats)
+        feats = self._packed[1]
+        new_res = ()
+        for res, blk in zip(down_block_res_samples, self.mmfs_down_blocks):
+            new_res += (res + blk(res, feats, mmfs_mask, spatial_shapes),)
+        sample = sample + self.mmfs_mid_block(sample, feats, mmfs_mask, spatial_shapes)
+        return sample, new_res

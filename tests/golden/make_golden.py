@@ -234,9 +234,52 @@ def make_llama(ref_ns):
     print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+# ---------------------------------------------------------------------------------------------
+# MMFSNet (decoders/sd_mmfs.py) -- tiny UNet skeleton: 2 resolution stages, 4 skip tensors + mid
+# ---------------------------------------------------------------------------------------------
+MMFSNET_TINY = dict(input_channel=64, block_out_channels=(32, 64), layers_per_block=1, downsample_factor=8)
+
+
+def mmfsnet_inputs(seed=11, B=2):
+    g = torch.Generator().manual_seed(seed)
+    res = [torch.randn((B, 32, 8, 8), generator=g), torch.randn((B, 32, 8, 8), generator=g),
+           torch.randn((B, 32, 4, 4), generator=g), torch.randn((B, 64, 4, 4), generator=g)]
+    sample = torch.randn((B, 64, 4, 4), generator=g)
+    feats = [torch.randn((B, 1, 64, s, s), generator=g) for s in (64, 32, 16, 8)]
+    mask = torch.ones((B, 1))
+    return sample, res, feats, mask
+
+
+def mmfsnet_state_dict(template, seed=808):
+    sd = seeded_state_dict(template, seed)
+    for k in sd:
+        if k.endswith("pos_embed"):
+            sd[k] = template[k].clone()                         # deterministic sin-cos table
+        if k.endswith("conv.weight"):
+            sd[k] = sd[k] * 4.0                                  # make the zero-initialised branch observable
+    return sd
+
+
+def make_mmfsnet(ref_ns):
+    net = ref_ns.sd_mmfs.MMFSNet(**MMFSNET_TINY).eval()
+    sd = mmfsnet_state_dict(net.state_dict())
+    net.load_state_dict(sd)
+    sample, res, feats, mask = mmfsnet_inputs()
+    with torch.no_grad():
+        out_sample, out_res = net(sample, res, feats, mask)
+    path = os.path.join(HERE, "mmfsnet_tiny.npz")
+    arrays = {"sample": out_sample.numpy(), "weight_checksum": np.array(float(sum(v.double().sum() for v in sd.values())))}
+    for i, r in enumerate(out_res):
+        arrays[f"res{i}"] = r.numpy()
+    np.savez_compressed(path, **arrays)
+    print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["msda", "mmfs", "llama"]
+    which = sys.argv[1:] or ["msda", "mmfs", "llama", "mmfsnet"]
+    if "mmfsnet" in which:
+        make_mmfsnet(ref_loader.load())
     if "llama" in which:
         make_llama(ref_loader.load())
     if "msda" in which:
