@@ -18,6 +18,8 @@ def test_greedy_generation_matches_oracle_loop():
     BOS, IMG, SOI = 1, 62, 63
     model = InterleavedForward(cfg, special_tokens=dict(bos_token_id=BOS, image_token_id=IMG, soi_token_id=SOI), orig_vocab_size=62)
     sd = seeded_state_dict(model.state_dict(), seed=31337)
+    sd["text_decoder.head.weight"][60:] = 0        # never emit the special ids: their logits stay 0 < max of 60 random logits
+    sd["text_decoder.head_new.weight"].zero_()
     model.load_state_dict(sd)
     g = torch.Generator().manual_seed(3)
     L, n_tok = 20, 3

