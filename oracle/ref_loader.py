@@ -101,4 +101,35 @@ def load():
                            os.path.join(root, "models", "decoders", "sd_mmfs.py"))
     except Exception as e:  # pragma: no cover
         ns.sd_mmfs_error = e
+    try:   # ViT-Adapter building blocks (need a timm stub: DropPath is never active at drop_path = 0)
+        if "timm" not in sys.modules:
+            timm = types.ModuleType("timm"); timm.models = types.ModuleType("timm.models")
+            timm.models.layers = types.ModuleType("timm.models.layers")
+            timm.models.layers.DropPath = type("DropPath", (torch_nn().Identity,), {"__init__": lambda self, p=0.0: torch_nn().Identity.__init__(self)})
+            sys.modules.update({"timm": timm, "timm.models": timm.models, "timm.models.layers": timm.models.layers})
+        enc = os.path.join(root, "models", "encoders")
+        _stub(f"{_PKG}.models.encoders", enc)
+        va = os.path.join(enc, "vit_adapter")
+        _stub(f"{_PKG}.models.encoders.vit_adapter", va)
+        vops = os.path.join(va, "ops")
+        _stub(f"{_PKG}.models.encoders.vit_adapter.ops", vops)
+        vf = _stub(f"{_PKG}.models.encoders.vit_adapter.ops.functions", os.path.join(vops, "functions"))
+        vfunc = _load(f"{_PKG}.models.encoders.vit_adapter.ops.functions.ms_deform_attn_func",
+                      os.path.join(vops, "functions", "ms_deform_attn_func.py"))
+        vf.MSDeformAttnFunction = _CoreFunction
+        vm = _stub(f"{_PKG}.models.encoders.vit_adapter.ops.modules", os.path.join(vops, "modules"))
+        vmod = _load(f"{_PKG}.models.encoders.vit_adapter.ops.modules.ms_deform_attn",
+                     os.path.join(vops, "modules", "ms_deform_attn.py"))
+        vmod.MSDeformAttnFunction = _CoreFunction
+        vm.MSDeformAttn = vmod.MSDeformAttn
+        ns.adapter = _load(f"{_PKG}.models.encoders.vit_adapter.adapter_modules", os.path.join(va, "adapter_modules.py"))
+        ns.adapter_msda = vmod
+    except Exception as e:  # pragma: no cover
+        ns.adapter = None
+        ns.adapter_error = e
     return ns
+
+
+def torch_nn():
+    import torch.nn as nn
+    return nn

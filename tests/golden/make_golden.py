@@ -275,9 +275,70 @@ def make_mmfsnet(ref_ns):
     print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+# ---------------------------------------------------------------------------------------------
+# ViT-Adapter building blocks (encoders/vit_adapter/adapter_modules.py): SpatialPriorModule and one
+# InteractionBlockWithCls with the two extra extractors; the CLIP blocks in between are replaced by a fixed
+# element-wise map so that only reference code under /root/reference is exercised.
+# ---------------------------------------------------------------------------------------------
+ADAPTER_TINY = dict(dim=256, heads=8, n_points=4, inplanes=16, H=4)     # deform_ratio 0.5 -> head size 16... see below
+
+
+class _FakeBlocks(torch.nn.Module):
+    """Stands in for the sliced CLIPEncoder: x -> tanh(x) * 1.5 (deterministic, parameter-free)."""
+
+    def forward(self, x):
+        import types as _t
+        return _t.SimpleNamespace(last_hidden_state=torch.tanh(x) * 1.5)
+
+
+def adapter_inputs(seed=21):
+    g = torch.Generator().manual_seed(seed)
+    c = ADAPTER_TINY
+    H = c["H"]
+    img = torch.rand((2, 3, H * 16, H * 16), generator=g)
+    x = torch.randn((2, H * H, c["dim"]), generator=g)
+    cls = torch.randn((2, 1, c["dim"]), generator=g)
+    return img, x, cls
+
+
+def adapter_state_dict(template, seed):
+    sd = seeded_state_dict(template, seed)
+    for k in list(sd):
+        if k.endswith("gamma"):
+            sd[k] = torch.full_like(sd[k], 0.7)                         # injector gamma is zero-initialised
+        if k.endswith("sampling_offsets.bias"):
+            sd[k] = sd[k] * 0.5
+    return sd
+
+
+def make_adapter(ref_ns):
+    ad = ref_ns.adapter
+    c = ADAPTER_TINY
+    spm = ad.SpatialPriorModule(inplanes=c["inplanes"], embed_dim=c["dim"]).eval()
+    blk = ad.InteractionBlockWithCls(dim=c["dim"], num_heads=c["heads"], n_points=c["n_points"], init_values=0.0, drop_path=0.0,
+                                     norm_layer=torch.nn.LayerNorm, with_cffn=True, cffn_ratio=0.25, deform_ratio=0.5,
+                                     with_cp=False, extra_extractor=True).eval()
+    sd_spm = adapter_state_dict(spm.state_dict(), 501)
+    sd_blk = adapter_state_dict(blk.state_dict(), 502)
+    spm.load_state_dict(sd_spm); blk.load_state_dict(sd_blk)
+    img, x, cls = adapter_inputs()
+    with torch.no_grad():
+        c1, c2, c3, c4 = spm(img)
+        d1, d2 = ad.deform_inputs(img)
+        cc = torch.cat([c2, c3, c4], dim=1)
+        xo, co, clso = blk(x, cc, cls, _FakeBlocks(), d1, d2, c["H"], c["H"])
+    path = os.path.join(HERE, "adapter_tiny.npz")
+    np.savez_compressed(path, c1=c1.numpy(), c2=c2.numpy(), c3=c3.numpy(), c4=c4.numpy(), x=xo.numpy(), c=co.numpy(),
+                        cls=clso.numpy(),
+                        checksum=np.array(float(sum(v.double().sum() for v in list(sd_spm.values()) + list(sd_blk.values())))))
+    print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["msda", "mmfs", "llama", "mmfsnet"]
+    which = sys.argv[1:] or ["msda", "mmfs", "llama", "mmfsnet", "adapter"]
+    if "adapter" in which:
+        make_adapter(ref_loader.load())
     if "mmfsnet" in which:
         make_mmfsnet(ref_loader.load())
     if "llama" in which:
