@@ -212,10 +212,9 @@ class InterleavedCfg3(Workload):
     """BASELINE cfg 3: the interleaved image-text forward on 4-image / 2048-token sequences, bf16 -- embed
     splice + image-visibility mask + MMFS feature packing (mm_interleaved.py:121-252), the 40-layer
     Llama-13B decoder with MMFS cross-attention in every 4th layer (modeling_llama_mmfs.py:623-752) and the
-    text head (decoder_text.py:140-163), i.e. the body of MMInterleaved.forward up to the logits.  The
-    visual tokenizer (CLIP ViT-L/14 + ViT-Adapter + Q-Former, ~1.3 % of the step's FLOPs) is not built yet:
-    its outputs (vis_embed, multiscale_features) are synthetic inputs of the step -- stated in
-    config.workload.  Random-init weights of the real architecture, synthetic token layout of SURVEY.md 8d."""
+    text head (decoder_text.py:140-163), i.e. the body of MMInterleaved.forward up to the logits, INCLUDING the
+    visual tokenizer (CLIP ViT-L/14 + ViT-Adapter + 12-layer Q-Former, visual_tokenizer.py:65-101) on the
+    4 x B images.  Random-init weights of the real architecture, synthetic token layout of SURVEY.md 8d."""
 
     name = "interleaved_cfg3"
     T, N_IMG, TOK_PER_IMG = 2048, 4, 64
@@ -238,9 +237,8 @@ class InterleavedCfg3(Workload):
             ids[:, s + 1:s + 1 + self.TOK_PER_IMG] = 32000
         ids[:, self.EXTRA_BOS_AT] = 1
         dt = torch.bfloat16
-        vis = (0.5 * torch.randn((B * self.N_IMG, self.TOK_PER_IMG, 5120), generator=g)).to(dt)
-        feats = [torch.randn((B * self.N_IMG, 1024, s, s), generator=g).to(dt) for s in (32, 16, 8)]
-        host = [ids, vis] + feats
+        images = torch.rand((B * self.N_IMG, 3, 224, 224), generator=g)          # [0,1] like the reference's image_tensors
+        host = [ids, images]
         self.host = [t.pin_memory() for t in host] if pin else host
 
     def setup(self):
@@ -274,6 +272,15 @@ class InterleavedCfg3(Workload):
                 if isinstance(mod, MMFS):
                     mod.scale_ratios = torch.tensor(mod._scale_list, device="cuda")
         self.model = model.eval()
+        from mm_interleaved_b200.visual_tokenizer import Injector, VisualTokenizer
+        torch.manual_seed(11)
+        tok = VisualTokenizer()                                  # ViT-L/14 + adapter + Q-Former(64 queries, 12 layers)
+        with torch.no_grad():
+            for mod in tok.modules():
+                if isinstance(mod, Injector):
+                    mod.gamma.fill_(0.5)                         # zero-initialised in the reference: make the branch count
+            tok.proj.weight.normal_(0.0, 0.02)
+        self.tok = tok.to("cuda", torch.bfloat16).eval()
         self.dev = [t.cuda() for t in self.host]
         self.nimg = torch.full((self.B,), self.N_IMG, dtype=torch.long, device="cuda")
         self.out_h = torch.empty((self.B, self.T), dtype=torch.long).pin_memory()
@@ -314,9 +321,10 @@ class InterleavedCfg3(Workload):
         return self.B
 
     def _forward(self, tensors):
-        ids, vis = tensors[0], tensors[1]
+        ids, images = tensors[0], tensors[1]
         with torch.no_grad():
-            logits = self.model(ids, {"vis_embed": vis, "multiscale_features": tensors[2:]}, self.nimg, self.N_IMG)
+            vis = self.tok(images.to(torch.bfloat16))
+            logits = self.model(ids, vis, self.nimg, self.N_IMG)
             return logits.argmax(-1)
 
     def step_device(self):
@@ -346,13 +354,12 @@ class InterleavedCfg3(Workload):
                 "attn_launches": len(t), "attn_avg_ms": sum(t) / len(t) if t else None}
 
     def config(self):
-        return {"workload": f"BASELINE cfg3 interleaved forward, {self.B} sequences/GPU x (4 images, 2048 tokens): embed splice + "
-                            "visibility mask + MMFS feature packing + Llama-13B decoder (40 layers, MMFS cross-attn every 4th) "
-                            "+ text head + argmax; visual-tokenizer outputs (vis_embed, 3 multi-scale maps) are synthetic "
-                            "inputs (tokenizer not built yet)",
+        return {"workload": f"BASELINE cfg3 interleaved forward, {self.B} sequences/GPU x (4 images 224^2, 2048 tokens): visual tokenizer "
+                            "(CLIP ViT-L/14 + ViT-Adapter + Q-Former) + embed splice + visibility mask + MMFS feature packing + "
+                            "Llama-13B decoder (40 layers, MMFS cross-attn every 4th) + text head + argmax",
                 "step_unit": "one 4-image/2048-token sequence forward",
                 "global_batch": self.B * self.world, "seq_len": self.T, "images_per_seq": self.N_IMG,
-                "parallelism": f"dp{self.world}", "params": "13B Llama + 10 MMFS layers, random init, bf16",
+                "parallelism": f"dp{self.world}", "params": "13B Llama + 10 MMFS layers + 0.45B visual tokenizer, random init, bf16",
                 "l2": "192 MiB buffer written between timed steps (L2 flush); weights (27 GB) exceed L2 anyway"}
 
     def roofline(self, kernel):
@@ -410,7 +417,9 @@ class InterleavedCfg3(Workload):
         if not hasattr(self, "_cpu"):
             ids = self.host[0][:1]
             x = torch.randn((1, self.T, 5120), generator=torch.Generator().manual_seed(5)) * 0.5
-            feats = pack_mmfs_features([f[:4].float() for f in self.host[2:]], [32, 16, 8], torch.tensor([4]), 4)
+            gf = torch.Generator().manual_seed(9)
+            feats = pack_mmfs_features([torch.randn((4, 1024, sz, sz), generator=gf) for sz in (32, 16, 8)], [32, 16, 8],
+                                       torch.tensor([4]), 4)
             cross = cross_attention_mask_from_ids(ids, 4, 1, 32001, torch.tensor([4]))
             cfg = dict(eps=1e-6, n_heads=40, n_layers=1, spatial_shapes=[(32, 32), (16, 16), (8, 8)])
             add_mask = additive_mask_ref(torch.ones((1, self.T)), self.T, 0, torch.float32)
@@ -430,7 +439,8 @@ class InterleavedCfg3(Workload):
     # < 2 % of the work), see reference_sample
     reference_step_fraction = None
     reference_sample = ("each step = 1 plain + 1 MMFS cross-attention decoder layer of 1 sequence (T=2048, 4 images) in fp32 "
-                        "through the oracle restatement; value = 1 / (30*t_plain + 10*t_cross)")
+                        "through the oracle restatement; value = 1 / (30*t_plain + 10*t_cross); the visual tokenizer, glue and "
+                        "text head (< 3 % of the FLOPs) are not in the CPU sample")
 
     def cpu_baseline(self):
         threads = min(os.cpu_count() or 1, 64)
