@@ -282,6 +282,21 @@ class InterleavedCfg3(Workload):
             tok.proj.weight.normal_(0.0, 0.02)
         self.tok = tok.to("cuda", torch.bfloat16).eval()
         self.dev = [t.cuda() for t in self.host]
+        # The tokenizer is ~2400 small launches for 16 images (launch-bound on the host): capture it once in a CUDA
+        # graph over static buffers and replay it every step.
+        self.tok_in = torch.zeros((self.B * self.N_IMG, 3, 224, 224), dtype=torch.bfloat16, device="cuda")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(3):
+                self.tok(self.tok_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        before = ops.launch_counter[0]
+        self.tok_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.tok_graph), torch.no_grad():
+            self.tok_out = self.tok(self.tok_in)
+        self.tok_graph_launches = ops.launch_counter[0] - before
         self.nimg = torch.full((self.B,), self.N_IMG, dtype=torch.long, device="cuda")
         self.out_h = torch.empty((self.B, self.T), dtype=torch.long).pin_memory()
         self.last = None
@@ -295,9 +310,11 @@ class InterleavedCfg3(Workload):
             self._sampler_events.append((e0, e1)); self._launches += 1
             return r
 
-        def timed_attn(*a, **k):
+        def timed_attn(q, *a, **k):
+            if q.shape[1] != self.T or q.shape[3] != 128 or torch.cuda.is_current_stream_capturing():
+                return orig_attn(q, *a, **k)                      # only the Llama prefill attention is the roofline subject
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); r = orig_attn(*a, **k); e1.record()
+            e0.record(); r = orig_attn(q, *a, **k); e1.record()
             self._attn_events.append((e0, e1))
             return r
 
@@ -323,8 +340,10 @@ class InterleavedCfg3(Workload):
     def _forward(self, tensors):
         ids, images = tensors[0], tensors[1]
         with torch.no_grad():
-            vis = self.tok(images.to(torch.bfloat16))
-            logits = self.model(ids, vis, self.nimg, self.N_IMG)
+            self.tok_in.copy_(images)                             # fp32 [0,1] images -> bf16 static buffer
+            self.tok_graph.replay()
+            self._launches += self.tok_graph_launches
+            logits = self.model(ids, self.tok_out, self.nimg, self.N_IMG)
             return logits.argmax(-1)
 
     def step_device(self):
@@ -360,7 +379,8 @@ class InterleavedCfg3(Workload):
                 "step_unit": "one 4-image/2048-token sequence forward",
                 "global_batch": self.B * self.world, "seq_len": self.T, "images_per_seq": self.N_IMG,
                 "parallelism": f"dp{self.world}", "params": "13B Llama + 10 MMFS layers + 0.45B visual tokenizer, random init, bf16",
-                "l2": "192 MiB buffer written between timed steps (L2 flush); weights (27 GB) exceed L2 anyway"}
+                "l2": "192 MiB buffer written between timed steps (L2 flush); weights (27 GB) exceed L2 anyway",
+                "cuda_graph": "visual tokenizer captured once and replayed per step; decoder eager"}
 
     def roofline(self, kernel):
         peaks = measured_peaks()

@@ -62,6 +62,59 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const T *__restrict__ x, c
 }
 
 // ---- LayerNorm (biased variance, fp32 statistics) ------------------------------------------------------
+// Warp per row: the row lives in registers (16-byte vector loads), mean and centred variance are two warp
+// reductions, one pass over HBM.  Rows of up to 32 * VEC * kLnChunks elements (2048 bf16 / 1024 fp32) take this
+// path -- every LayerNorm on the interleaved path (64 ... 1280 columns); longer or unaligned rows use the block kernel.
+constexpr int kLnChunks = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_warp_kernel(const T *__restrict__ x, const T *__restrict__ w,
+                                                              const T *__restrict__ b, T *__restrict__ y, long rows, int cols, float eps) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const T *xr = x + row * cols;
+    T *yr = y + row * cols;
+    const int nvec = cols / VEC;                 // host guarantees cols % VEC == 0 and nvec <= 32 * kLnChunks
+    float v[kLnChunks][VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < kLnChunks; ++c) {
+        const int i = lane + 32 * c;
+        if (i < nvec) {
+            Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(xr + i * VEC), v[c]);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) s += v[c][k];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)cols;
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < kLnChunks; ++c)
+        if (lane + 32 * c < nvec) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) { const float d = v[c][k] - mean; ss += d * d; }
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float r = rsqrtf(ss / (float)cols + eps);
+#pragma unroll
+    for (int c = 0; c < kLnChunks; ++c) {
+        const int i = lane + 32 * c;
+        if (i < nvec) {
+            float g[VEC], bb[VEC], o[VEC];
+            if (w) Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(w + i * VEC), g);
+            if (b) Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(b + i * VEC), bb);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) o[k] = (v[c][k] - mean) * r * (w ? g[k] : 1.f) + (b ? bb[k] : 0.f);
+            *reinterpret_cast<uint4 *>(yr + i * VEC) = Vec16<T>::pack(o);
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) layernorm_kernel(const T *__restrict__ x, const T *__restrict__ w,
                                                          const T *__restrict__ b, T *__restrict__ y, int cols, float eps) {
@@ -143,9 +196,16 @@ static int launch_all(int which, const void *a, const void *b, const void *c, vo
         case 0:   // rmsnorm: a=x b=w d=y n0=rows i0=cols
             rmsnorm_kernel<T><<<(unsigned)n0, 256, 0, st>>>((const T *)a, (const T *)b, (T *)d, i0, eps);
             break;
-        case 1:   // layernorm: a=x b=w c=bias d=y
-            layernorm_kernel<T><<<(unsigned)n0, 256, 0, st>>>((const T *)a, (const T *)b, (const T *)c, (T *)d, i0, eps);
+        case 1: { // layernorm: a=x b=w c=bias d=y
+            constexpr int VEC = 16 / (int)sizeof(T);
+            const bool vec_ok = (i0 % VEC == 0) && (i0 / VEC <= 32 * kLnChunks) &&
+                                (((uintptr_t)a | (uintptr_t)d | (uintptr_t)b | (uintptr_t)c) % 16 == 0);
+            if (vec_ok)
+                layernorm_warp_kernel<T><<<(unsigned)((n0 + 7) / 8), 256, 0, st>>>((const T *)a, (const T *)b, (const T *)c, (T *)d, n0, i0, eps);
+            else
+                layernorm_kernel<T><<<(unsigned)n0, 256, 0, st>>>((const T *)a, (const T *)b, (const T *)c, (T *)d, i0, eps);
             break;
+        }
         case 2: { // rope: d=q (in place), a=k (in place, cast away const), e=cos f=sin c=pos; n0=tokens i0=H i1=hd i2=q_stride i3=k_stride i4=pos_per_batch i5=T
             const long total = n0 * i0 * 2 * ((i1 / 2) / (16 / (int)sizeof(T)));
             const int grid = (int)((total + 255) / 256 < 148L * 16 ? (total + 255) / 256 : 148L * 16);

@@ -42,12 +42,28 @@ def sincos_pos_embed_2d(embed_dim: int, grid_size: int) -> torch.Tensor:
     return torch.from_numpy(np.concatenate([enc(rows), enc(cols)], axis=1)).float()
 
 
+_RESIZE_CACHE = {}
+
+
 def resize_abs_pos(abs_pos: torch.Tensor, tgt_len: int) -> torch.Tensor:
-    """``get_abs_pos`` (utils/pos_embed.py:16-40) for embeddings without a cls token: bicubic resize of the square grid."""
+    """``get_abs_pos`` (utils/pos_embed.py:16-40) for embeddings without a cls token: bicubic resize of the square grid.
+    The table is a frozen parameter, so the resized copy is cached (the reference re-interpolates on every forward)."""
     src = int(math.sqrt(abs_pos.shape[0]))
     tgt = int(math.sqrt(tgt_len))
     if src == tgt:
         return abs_pos
+    key = (abs_pos.data_ptr(), abs_pos._version, abs_pos.dtype, abs_pos.device, tuple(abs_pos.shape), tgt)
+    if key in _RESIZE_CACHE:
+        return _RESIZE_CACHE[key]
+    if len(_RESIZE_CACHE) > 64:
+        _RESIZE_CACHE.clear()
+    out = _resize_abs_pos_uncached(abs_pos, src, tgt)
+    if not torch.is_grad_enabled() or not abs_pos.requires_grad:
+        _RESIZE_CACHE[key] = out
+    return out
+
+
+def _resize_abs_pos_uncached(abs_pos, src, tgt):
     x = abs_pos.float().reshape(1, src, src, -1).permute(0, 3, 1, 2)
     x = F.interpolate(x, size=(tgt, tgt), mode="bicubic", align_corners=False)
     return x.permute(0, 2, 3, 1).flatten(0, 2).to(abs_pos.dtype)

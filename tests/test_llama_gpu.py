@@ -138,3 +138,20 @@ def test_model_bf16_tracks_fp32_reference():
     valid = attn_mask.bool()
     err = (out.last_hidden_state.float().cpu() - ref).abs()[valid]
     assert err.max() <= 6e-2 * ref[valid].abs().max()      # bf16 storage through 3 layers
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cols", [64, 320, 768, 1024, 1280, 2048, 5120, 100])
+def test_layernorm_matches_torch(cols, dtype):
+    """Warp-per-row path (cols <= 2048 bf16 / 1024 fp32, 16-byte aligned) and the block fallback (5120, 100)."""
+    from mm_interleaved_b200 import ops
+    g = torch.Generator().manual_seed(cols)
+    x = (torch.randn((3, 37, cols), generator=g) * 2 + 0.5).to(dtype)
+    w = (1 + 0.1 * torch.randn(cols, generator=g)).to(dtype)
+    b = (0.1 * torch.randn(cols, generator=g)).to(dtype)
+    y = ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV), 1e-6).float().cpu()
+    ref = torch.nn.functional.layer_norm(x.float(), (cols,), w.float(), b.float(), 1e-6)
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    assert (y - ref).abs().max() <= tol
+    y2 = ops.layernorm(x.to(DEV), None, None, 1e-6).float().cpu()
+    assert (y2 - torch.nn.functional.layer_norm(x.float(), (cols,), None, None, 1e-6)).abs().max() <= tol
