@@ -246,3 +246,34 @@ def test_dropin_module_and_autograd_wrapper():
     # mixed dtypes (autocast-style): loc/weights fp32, value fp16 -> cast to value dtype
     o3 = m.MSDeformAttnFunction.apply(args[0].half(), args[1], args[2], args[3], args[4], 1)
     assert o3.dtype == torch.float16
+
+
+def _ref_op():
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref (the reference's own CUDA op) was not built")
+    return ref_cuda.load()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.float64])
+@pytest.mark.parametrize("case", [0, 1, 2, 3, 5])
+def test_against_the_reference_cuda_op(case, dtype):
+    """The reference's OWN kernel (ops/src/cuda/ms_deform_im2col_cuda.cuh, compiled unmodified for sm_100a by
+    oracle/build_ref.py) run on the same B200 on the same inputs."""
+    ref = _ref_op()
+    m = _mod()
+    N, shapes, M, D, Lq, P = CASES[case]
+    v, s, st, loc, a = make_msda_inputs(N, shapes, M, D, Lq, P, seed=300 + case, loc_mode="clustered", dtype=dtype)
+    args = [v.to(DEV, dtype), s.to(DEV), st.to(DEV), loc.to(DEV, dtype), a.to(DEV, dtype)]
+    want = ref.ms_deform_attn_forward(*args, 64)
+    got = m.ms_deform_attn_forward(*args, 64)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape and got.dtype == want.dtype
+    if dtype == torch.float64:
+        assert (got - want).abs().max() <= 1e-12
+    elif dtype == torch.float32:
+        assert (got - want).abs().max() <= 2e-6            # fp32 re-association only
+    else:
+        diff = (got.float() - want.float()).abs()
+        assert (diff <= want.float().abs() * 2.0 ** -10 + 1e-7).all()      # both round one fp32 accumulator: <= 1 fp16 ulp
+        assert (got == want).float().mean() > 0.97
