@@ -74,6 +74,20 @@ int mmfs_msda_forward(const void *value, const int64_t *spatial_shapes, const in
                       int dtype, unsigned flags, void *stream);
 
 /*
+ * Multi-scale deformable attention backward (training path).
+ * Replaces ms_deform_attn_backward / ms_deform_attn_cuda_backward (ops/src/ms_deform_attn.h:41-61,
+ * ops/src/cuda/ms_deform_attn_cuda.cu:84-166) and the col2im kernels (ops/src/cuda/ms_deform_im2col_cuda.cuh:304-923).
+ * grad_out (N, Lq, M*D) dtype.  The three gradient buffers are FP32 (the reference also accumulates half
+ * inputs in fp32 and casts afterwards, cu:122-129,156-160): grad_value (N,S,M,D) must be ZERO-INITIALISED by the
+ * caller (it is accumulated with atomics, as in the reference); grad_loc (N,Lq,M,L,P,2) and grad_attn (N,Lq,M,L,P)
+ * are fully overwritten.  dtype f32 / f16 / bf16; D in {32, 64, 128}.
+ */
+int mmfs_msda_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start,
+                       const void *sampling_loc, const void *attn_weight, const void *grad_out,
+                       float *grad_value, float *grad_loc, float *grad_attn,
+                       int N, int S, int M, int D, int L, int Lq, int P, int dtype, void *stream);
+
+/*
  * Integer index stream of the sampler, for parity checking of the sampling-point index
  * math (same device function as the forward kernels use).  idx is int32
  * (N, Lq, M, L, P, 8) = [in_range, h_low, w_low, valid_mask(bit k = corner k+1 fetched),

@@ -80,15 +80,26 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
 
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
                             grad_output, im2col_step: int = 64):
-    """``MSDA.ms_deform_attn_backward`` (ops/src/ms_deform_attn.h:41-61) -- training only.
-
-    SURVEY.md section 8 marks the backward kernels out of scope for the forward hot path
-    (section 8f rank 4, "next"); the symbol exists so the autograd wrapper imports, and
-    fails loudly instead of silently computing something else.
-    """
-    raise NotImplementedError(
-        "ms_deform_attn_backward: the B200 build covers the forward (inference) hot path; "
-        "the backward kernels are a later row of SURVEY.md section 8f")
+    """Drop-in for ``MSDA.ms_deform_attn_backward`` (ops/src/ms_deform_attn.h:41-61): returns
+    ``[grad_value, grad_sampling_loc, grad_attn_weight]`` shaped and typed like the inputs.  Gradients are accumulated
+    in fp32 and cast back for 16-bit inputs exactly like the reference host code (cu:122-129, 156-160).  fp64 inputs
+    are not implemented (the reference uses them only as ground truth in its test scripts)."""
+    N, S, M, D, L, Lq, P = _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step)
+    _require(grad_output.is_cuda and grad_output.is_contiguous() and grad_output.dtype == value.dtype and
+             tuple(grad_output.shape) == (N, Lq, M * D), "grad_output must be a contiguous CUDA tensor (N, Lq, M*D) of value's dtype")
+    if value.dtype == torch.float64:
+        raise NotImplementedError("ms_deform_attn_backward: float64 is not implemented on the B200 path")
+    gv = torch.zeros((N, S, M, D), dtype=torch.float32, device=value.device)
+    gl = torch.empty((N, Lq, M, L, P, 2), dtype=torch.float32, device=value.device)
+    ga = torch.empty((N, Lq, M, L, P), dtype=torch.float32, device=value.device)
+    if N > 0 and Lq > 0:
+        with torch.cuda.device(value.device):
+            rc = _lib.lib().mmfs_msda_backward(
+                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+                attn_weight.data_ptr(), grad_output.data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr(),
+                N, S, M, D, L, Lq, P, _DTYPE_CODE[value.dtype], torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "ms_deform_attn_backward")
+    return [gv.to(value.dtype), gl.to(value.dtype), ga.to(value.dtype)]
 
 
 def msda_index_stream(spatial_shapes, level_start_index, sampling_loc, M: int, D: int) -> torch.Tensor:

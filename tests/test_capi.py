@@ -52,7 +52,7 @@ def test_python_shim_mirrors_reference_errors():
         MSDA.ms_deform_attn_forward(v, s, st, loc, a, 1)
     with pytest.raises(RuntimeError, match="contiguous"):                    # cu:29
         MSDA.ms_deform_attn_forward(v.transpose(1, 2), s, st, loc, a, 1)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
         MSDA.ms_deform_attn_backward(v, s, st, loc, a, torch.zeros(2, 3, 16), 1)
 
 
