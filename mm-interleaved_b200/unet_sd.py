@@ -1,0 +1,290 @@
+"""SD-2.1-base UNet denoise step with the MMFS conditioning hook, B200-native assembly.
+
+The reference does not contain the UNet arithmetic: it monkey-patches diffusers 0.20.0's
+``UNet2DConditionModel.forward`` (utils/monkey_patch/sd_unet_forward_monkey_patch.py:17-371) to take three
+extra keyword arguments -- ``mmfs_features``, ``mmfs_mask``, ``mmfs_module`` -- and to call
+``mmfs_module(sample, down_block_res_samples, mmfs_features, mmfs_mask)`` between the mid block and the up blocks
+(:316-326).  diffusers is neither under /root/reference nor in this image, so this file restates the published
+SD-2.1-base architecture (block_out_channels (320, 640, 1280, 1280), 2 res-layers per block, 5/10/20/20 heads of
+64, cross-attention dim 1024, linear projections, GEGLU feed-forward, GroupNorm(32)) with diffusers' parameter
+naming so that a reference checkpoint's ``unet.*`` keys map one-to-one, and keeps the patched forward's
+signature.  **Parity is unpinned** (no reference-side test, golden vector or importable implementation exists
+here); the block-level formulas are checked against plain PyTorch statements in tests/test_unet_gpu.py.
+
+B200 side: every self- and cross-attention runs in this repo's tcgen05 kernel (T in {4096, 1024, 256, 64},
+head size 64, kv = 77 for cross attention), the MMFS branch in the fused sampler (sd_mmfs.py), LayerNorms in the
+warp-per-row kernel; convolutions / GroupNorm are library calls (cuDNN, channels-last) -- the conv-as-GEMM tcgen05
+kernel of SURVEY.md section 7 step 5 is not built.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+
+
+def timestep_embedding(timesteps: torch.Tensor, dim: int, max_period: int = 10000) -> torch.Tensor:
+    """diffusers ``Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0)``: [cos | sin] of t * 10000^(-i/half)."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=timesteps.device) / half)
+    args = timesteps[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+class TimestepEmbedding(nn.Module):
+    def __init__(self, in_channels, time_embed_dim):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_channels, time_embed_dim)
+        self.linear_2 = nn.Linear(time_embed_dim, time_embed_dim)
+
+    def forward(self, x):
+        return self.linear_2(F.silu(self.linear_1(x)))
+
+
+class ResnetBlock2D(nn.Module):
+    def __init__(self, in_channels, out_channels, temb_channels=1280, groups=32, eps=1e-5):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, in_channels, eps=eps)
+        self.conv1 = nn.Conv2d(in_channels, out_channels, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb_channels, out_channels)
+        self.norm2 = nn.GroupNorm(groups, out_channels, eps=eps)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, 3, padding=1)
+        self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else None
+
+    def forward(self, x, temb):
+        h = self.conv1(F.silu(self.norm1(x)))
+        h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
+        h = self.conv2(F.silu(self.norm2(h)))
+        return (x if self.conv_shortcut is None else self.conv_shortcut(x)) + h
+
+
+class Attention(nn.Module):
+    """diffusers ``Attention`` (to_q / to_k / to_v without bias, to_out.0 with bias); softmax(q k^T / sqrt(d)) v."""
+
+    def __init__(self, query_dim, cross_attention_dim=None, heads=8, dim_head=64):
+        super().__init__()
+        inner = heads * dim_head
+        self.heads, self.dim_head = heads, dim_head
+        kv = cross_attention_dim or query_dim
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(kv, inner, bias=False)
+        self.to_v = nn.Linear(kv, inner, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(inner, query_dim), nn.Dropout(0.0)])
+
+    def forward(self, x, context=None):
+        B, T, _ = x.shape
+        ctx = x if context is None else context
+        q = self.to_q(x).view(B, T, self.heads, self.dim_head)
+        k = self.to_k(ctx).view(B, ctx.shape[1], self.heads, self.dim_head)
+        v = self.to_v(ctx).view(B, ctx.shape[1], self.heads, self.dim_head)
+        return self.to_out[0](ops.attention(q, k, v, causal=False))
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def forward(self, x):
+        h, gate = self.proj(x).chunk(2, dim=-1)
+        return h * F.gelu(gate)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, mult=4):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
+
+    def forward(self, x):
+        return self.net[2](self.net[0](x))
+
+
+class BasicTransformerBlock(nn.Module):
+    def __init__(self, dim, heads, dim_head, cross_attention_dim):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn1 = Attention(dim, None, heads, dim_head)
+        self.norm2 = nn.LayerNorm(dim)
+        self.attn2 = Attention(dim, cross_attention_dim, heads, dim_head)
+        self.norm3 = nn.LayerNorm(dim)
+        self.ff = FeedForward(dim)
+
+    @staticmethod
+    def _ln(mod, x):
+        return ops.layernorm(x.contiguous(), mod.weight, mod.bias, mod.eps)
+
+    def forward(self, x, context):
+        x = x + self.attn1(self._ln(self.norm1, x))
+        x = x + self.attn2(self._ln(self.norm2, x), context)
+        return x + self.ff(self._ln(self.norm3, x))
+
+
+class Transformer2DModel(nn.Module):
+    def __init__(self, heads, dim_head, in_channels, cross_attention_dim, groups=32):
+        super().__init__()
+        inner = heads * dim_head
+        self.norm = nn.GroupNorm(groups, in_channels, eps=1e-6)
+        self.proj_in = nn.Linear(in_channels, inner)                       # use_linear_projection=True (SD 2.x)
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(inner, heads, dim_head, cross_attention_dim)])
+        self.proj_out = nn.Linear(inner, in_channels)
+
+    def forward(self, x, context):
+        B, C, H, W = x.shape
+        h = self.norm(x).permute(0, 2, 3, 1).reshape(B, H * W, C)
+        h = self.proj_in(h)
+        for blk in self.transformer_blocks:
+            h = blk(h, context)
+        h = self.proj_out(h).reshape(B, H, W, C).permute(0, 3, 1, 2)
+        return h + x
+
+
+class Downsample2D(nn.Module):
+    def __init__(self, channels):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, channels, 3, stride=2, padding=1)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class Upsample2D(nn.Module):
+    def __init__(self, channels):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, channels, 3, padding=1)
+
+    def forward(self, x):
+        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
+class DownBlock(nn.Module):
+    def __init__(self, cin, cout, temb, heads, cross_dim, with_attn, add_down, layers=2):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, temb) for i in range(layers)])
+        self.attentions = nn.ModuleList([Transformer2DModel(heads, cout // heads, cout, cross_dim) for _ in range(layers)]) if with_attn else None
+        self.downsamplers = nn.ModuleList([Downsample2D(cout)]) if add_down else None
+
+    def forward(self, x, temb, context):
+        outs = ()
+        for i, res in enumerate(self.resnets):
+            x = res(x, temb)
+            if self.attentions is not None:
+                x = self.attentions[i](x, context)
+            outs += (x,)
+        if self.downsamplers is not None:
+            x = self.downsamplers[0](x)
+            outs += (x,)
+        return x, outs
+
+
+class MidBlock(nn.Module):
+    def __init__(self, ch, temb, heads, cross_dim):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(ch, ch, temb), ResnetBlock2D(ch, ch, temb)])
+        self.attentions = nn.ModuleList([Transformer2DModel(heads, ch // heads, ch, cross_dim)])
+
+    def forward(self, x, temb, context):
+        x = self.resnets[0](x, temb)
+        x = self.attentions[0](x, context)
+        return self.resnets[1](x, temb)
+
+
+class UpBlock(nn.Module):
+    def __init__(self, cin, cout, prev, temb, heads, cross_dim, with_attn, add_up, layers=3):
+        super().__init__()
+        res = []
+        for i in range(layers):
+            skip = cin if i == layers - 1 else cout
+            inp = prev if i == 0 else cout
+            res.append(ResnetBlock2D(inp + skip, cout, temb))
+        self.resnets = nn.ModuleList(res)
+        self.attentions = nn.ModuleList([Transformer2DModel(heads, cout // heads, cout, cross_dim) for _ in range(layers)]) if with_attn else None
+        self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if add_up else None
+
+    def forward(self, x, res_samples, temb, context):
+        for i, res in enumerate(self.resnets):
+            x = res(torch.cat([x, res_samples.pop()], dim=1), temb)
+            if self.attentions is not None:
+                x = self.attentions[i](x, context)
+        if self.upsamplers is not None:
+            x = self.upsamplers[0](x)
+        return x
+
+
+class UNet2DConditionModel(nn.Module):
+    """SD-2.1-base UNet with the reference's patched forward signature (sd_unet_forward_monkey_patch.py:17-34)."""
+
+    def __init__(self, in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2,
+                 attention_head_dim=(5, 10, 20, 20), cross_attention_dim=1024):
+        super().__init__()
+        ch = list(block_out_channels)
+        temb = ch[0] * 4
+        self.block_out_channels = ch
+        self.conv_in = nn.Conv2d(in_channels, ch[0], 3, padding=1)
+        self.time_embedding = TimestepEmbedding(ch[0], temb)
+        self.down_blocks = nn.ModuleList()
+        cin = ch[0]
+        for i, cout in enumerate(ch):
+            last = i == len(ch) - 1
+            self.down_blocks.append(DownBlock(cin, cout, temb, attention_head_dim[i], cross_attention_dim,
+                                              with_attn=not last, add_down=not last, layers=layers_per_block))
+            cin = cout
+        self.mid_block = MidBlock(ch[-1], temb, attention_head_dim[-1], cross_attention_dim)
+        self.up_blocks = nn.ModuleList()
+        rev = list(reversed(ch))
+        rev_heads = list(reversed(attention_head_dim))
+        prev = rev[0]
+        for i, cout in enumerate(rev):
+            cin_skip = rev[min(i + 1, len(ch) - 1)]
+            self.up_blocks.append(UpBlock(cin_skip, cout, prev, temb, rev_heads[i], cross_attention_dim,
+                                          with_attn=i != 0, add_up=i != len(ch) - 1, layers=layers_per_block + 1))
+            prev = cout
+        self.conv_norm_out = nn.GroupNorm(32, ch[0], eps=1e-5)
+        self.conv_out = nn.Conv2d(ch[0], out_channels, 3, padding=1)
+
+    def forward(self, sample, timestep, encoder_hidden_states, mmfs_features: Optional[List[torch.Tensor]] = None,
+                mmfs_mask: Optional[torch.Tensor] = None, mmfs_module=None):
+        if not torch.is_tensor(timestep):
+            timestep = torch.tensor([timestep], device=sample.device)
+        t = timestep.reshape(-1).expand(sample.shape[0])
+        emb = self.time_embedding(timestep_embedding(t, self.block_out_channels[0]).to(sample.dtype))
+        sample = self.conv_in(sample)
+        res = (sample,)
+        for blk in self.down_blocks:
+            sample, outs = blk(sample, emb, encoder_hidden_states)
+            res += outs
+        sample = self.mid_block(sample, emb, encoder_hidden_states)
+        if mmfs_module is not None:                                      # the hook of :316-326
+            sample, res = mmfs_module(sample, res, mmfs_features, mmfs_mask)
+        res = list(res)
+        for blk in self.up_blocks:
+            sample = blk(sample, res, emb, encoder_hidden_states)
+        return self.conv_out(F.silu(self.conv_norm_out(sample)))
+
+
+@torch.no_grad()
+def denoise_loop(unet, latents, cond, uncond, mmfs_features, mmfs_mask, mmfs_module, num_steps=50, guidance=7.5,
+                 num_train_timesteps=1000):
+    """Classifier-free-guidance denoise loop in the shape of the patched pipeline ``__call__``
+    (utils/monkey_patch/sd_pipeline_monkey_patch.py:172-226: CFG duplicates the MMFS inputs, one UNet call on the
+    2B batch per step, ``uncond + g (text - uncond)``).  The scheduler arithmetic belongs to diffusers; a
+    deterministic DDIM (eta = 0) update on the SD 'scaled_linear' beta schedule stands in for it here."""
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, num_train_timesteps, dtype=torch.float64) ** 2
+    acp = torch.cumprod(1.0 - betas, 0).float().to(latents.device)
+    ts = torch.linspace(num_train_timesteps - 1, 0, num_steps).round().long().to(latents.device)
+    ctx = torch.cat([uncond, cond], 0)
+    feats2 = [torch.cat([f, f], 0) for f in mmfs_features] if mmfs_features is not None else None
+    mask2 = torch.cat([mmfs_mask, mmfs_mask], 0) if mmfs_mask is not None else None
+    for i, t in enumerate(ts):
+        eps = unet(torch.cat([latents, latents], 0), t, ctx, mmfs_features=feats2, mmfs_mask=mask2, mmfs_module=mmfs_module)
+        e_u, e_c = eps.chunk(2)
+        eps = (e_u + guidance * (e_c - e_u)).float()
+        a_t = acp[t]
+        a_prev = acp[ts[i + 1]] if i + 1 < len(ts) else torch.ones((), device=latents.device)
+        x0 = (latents.float() - (1 - a_t).sqrt() * eps) / a_t.sqrt()
+        latents = (a_prev.sqrt() * x0 + (1 - a_prev).sqrt() * eps).to(latents.dtype)
+    return latents
