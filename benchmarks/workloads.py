@@ -474,7 +474,114 @@ class InterleavedCfg3(Workload):
                           "restatement of the reference forward; scaled to 30 plain + 10 cross layers"}
 
 
-WORKLOADS = {"msda_cfg3": MsdaCfg3, "interleaved_cfg3": InterleavedCfg3}
+class SdCfg4(Workload):
+    """BASELINE cfg 4: SD-2.1 UNet 50-step classifier-free-guidance denoise at 512^2 (latents 64^2) with MMFS
+    conditioning on one context image, batch 8 per GPU (16 with CFG).  Non-default workload (`--workload sd_cfg4`);
+    a step = one full 50-step denoise of the local batch, unit = images/s."""
+
+    name = "sd_cfg4"
+    metric = "sd_unet_denoise_images_per_sec"
+    unit = "images/s"
+    STEPS = 50
+
+    def setup(self):
+        import mm_interleaved_b200 as m
+        from mm_interleaved_b200 import ops, unet_sd
+        self.m, self.ops, self.unet_sd = m, ops, unet_sd
+        self.B = self.local_batch or 8
+        torch.manual_seed(42 + self.rank)                                 # sd_base_seed: 42 (mm_inference.yaml:23)
+        dt = torch.bfloat16
+        self.unet = unet_sd.UNet2DConditionModel().to("cuda", dt).eval().to(memory_format=torch.channels_last)
+        net = m.MMFSNet(1024, (320, 640, 1280, 1280), 2)
+        with torch.no_grad():
+            for blk in list(net.mmfs_down_blocks) + [net.mmfs_mid_block]:
+                blk.conv.weight.normal_(0, 0.02)                          # zero-initialised in the reference
+        self.net = net.to("cuda", dt).eval()
+        g = torch.Generator().manual_seed(42)
+        self.host = [torch.randn((self.B, 4, 64, 64), generator=g), torch.randn((self.B, 77, 1024), generator=g) * 0.02] + \
+                    [torch.randn((self.B, 1, 1024, s, s), generator=g) for s in (64, 32, 16, 8)]
+        self.host = [t.to(dt).pin_memory() for t in self.host]
+        self.dev = [t.cuda() for t in self.host]
+        self.mask = torch.ones((self.B, 1), device="cuda")
+        self.out_h = torch.empty((self.B, 4, 64, 64), dtype=dt).pin_memory()
+        self._attn_events = []
+        orig = ops.attention
+
+        def timed(q, *a, **k):
+            if q.shape[1] != 4096:
+                return orig(q, *a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = orig(q, *a, **k); e1.record()
+            self._attn_events.append((e0, e1))
+            return r
+
+        unet_sd.ops.attention = timed
+        self.reset_counters()
+
+    def reset_counters(self):
+        super().reset_counters()
+        self._attn_events = []
+        if hasattr(self, "ops"):
+            self.ops.launch_counter[0] = 0
+
+    def launch_count(self):
+        return self.ops.launch_counter[0]
+
+    def units_per_step(self):
+        return self.B
+
+    def _run(self, t):
+        lat, cond, feats = t[0], t[1], list(t[2:])
+        return self.unet_sd.denoise_loop(self.unet, lat, cond, torch.zeros_like(cond), feats, self.mask, self.net,
+                                         num_steps=self.STEPS, guidance=7.5)
+
+    def step_device(self):
+        self.last = self._run(self.dev)
+
+    def step_e2e(self):
+        dev = [t.to("cuda", non_blocking=True) for t in self.host]
+        self.last = self._run(dev)
+        self.out_h.copy_(self.last, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def result_checksum(self):
+        return self.last.float().sum().reshape(1)
+
+    def h2d_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self.host)
+
+    def d2h_bytes(self):
+        return self.out_h.numel() * self.out_h.element_size()
+
+    def kernel_stats(self):
+        torch.cuda.synchronize()
+        t = [a.elapsed_time(b) for a, b in self._attn_events]
+        return {"launches": len(t), "avg_ms": sum(t) / len(t) if t else None}
+
+    def config(self):
+        return {"workload": f"BASELINE cfg4: SD-2.1-base UNet (866 M params, random init) {self.STEPS}-step CFG denoise, latents "
+                            f"({2 * self.B},4,64,64), ctx (77,1024), MMFSNet (13 blocks) on 1 context image; DDIM update as scheduler "
+                            "stand-in; convs / GroupNorm = cuDNN, attention + MMFS = this repo's kernels",
+                "step_unit": "one 512^2 image (50 UNet evaluations at batch 2 for CFG)", "global_batch": self.B * self.world,
+                "parallelism": f"dp{self.world}", "l2": "192 MiB buffer written between timed steps"}
+
+    def roofline(self, kernel):
+        peaks = measured_peaks()
+        flops = 4.0 * (2 * self.B) * 4096 * 4096 * 320                   # self-attn at T=4096, C=320 (5 x 64), plus kv=77 cross (small)
+        t = kernel["avg_ms"] * 1e-3 if kernel["avg_ms"] else None
+        return {"kernel": "attn_fwd_kernel<bf16,64> (tcgen05), UNet self/cross attention at T=4096", "bound": "tensor",
+                "achieved": flops / t / 1e12 if t else None, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": flops / t / 1e12 / peaks["bf16_tflops_sustained"] if t else None,
+                "note": "average over self (T_kv=4096) and cross (T_kv=77) calls; flops counted for the self-attention call",
+                "avg_launch_us": t * 1e6 if t else None, "launches_timed": kernel["launches"], "traffic": None}
+
+    def cpu_baseline(self):
+        return {"value": None, "unit": self.unit, "cores": 0, "kind": "port",
+                "sample": "no CPU restatement of the diffusers UNet exists in this repo (parity unpinned, DESIGN.md); "
+                          "the MMFS branch alone is covered by oracle/sd_mmfs.py"}
+
+
+WORKLOADS = {"msda_cfg3": MsdaCfg3, "interleaved_cfg3": InterleavedCfg3, "sd_cfg4": SdCfg4}
 AUTO = "interleaved_cfg3"
 
 

@@ -29,7 +29,7 @@ def test_unet_kernels_vs_torch_statements_and_hook(monkeypatch):
     torch.manual_seed(0)
     unet = unet_sd.UNet2DConditionModel(block_out_channels=(64, 128), layers_per_block=1, attention_head_dim=(2, 4),
                                         cross_attention_dim=96).to(DEV).eval()
-    net = m.MMFSNet(96, (64, 128), 1, downsample_factor=4, spatial_shapes=[16, 8, 4, 2]).to(DEV).eval()
+    net = m.MMFSNet(96, (64, 128), 1, downsample_factor=2, spatial_shapes=[16, 8, 4, 2]).to(DEV).eval()
     with torch.no_grad():
         for blk in list(net.mmfs_down_blocks) + [net.mmfs_mid_block]:
             blk.conv.weight.normal_(0, 0.2)
