@@ -397,7 +397,10 @@ class InterleavedCfg3(Workload):
                 "frac": achieved / peaks["hbm_gbs"] if achieved else None,
                 "algorithmic_bytes_per_launch": ab, "fused_kernel_bytes_per_launch": fused,
                 "achieved_fused_bytes_GBs": fused / t / 1e9 if t else None,
-                "avg_launch_us": t * 1e6 if t else None, "launches_timed": kernel["launches"], "traffic": None,
+                "avg_launch_us": t * 1e6 if t else None, "launches_timed": kernel["launches"],
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch (B = 4) from the committed capture
+                # profiles/r01_sampler_cfg3_fused_ncu_details.txt (ncu --set full): 20.93 MB + 10.75 MB
+                "traffic": 31.68e6 * self.B / 4.0,
                 "attention": {"kernel": "attn_fwd_kernel<bf16,128> (tcgen05)", "bound": "tensor",
                               "achieved": flops / ta / 1e12 if ta else None, "peak": peaks["bf16_tflops_sustained"],
                               "unit": "TFLOP/s", "frac": flops / ta / 1e12 / peaks["bf16_tflops_sustained"] if ta else None,
@@ -507,11 +510,11 @@ class SdCfg4(Workload):
         self._attn_events = []
         orig = ops.attention
 
-        def timed(q, *a, **k):
-            if q.shape[1] != 4096:
-                return orig(q, *a, **k)
+        def timed(q, kk, *a, **k):
+            if q.shape[1] != 4096 or kk.shape[1] != 4096:           # only the T = 4096 self-attention is the roofline subject
+                return orig(q, kk, *a, **k)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); r = orig(q, *a, **k); e1.record()
+            e0.record(); r = orig(q, kk, *a, **k); e1.record()
             self._attn_events.append((e0, e1))
             return r
 
@@ -569,10 +572,10 @@ class SdCfg4(Workload):
         peaks = measured_peaks()
         flops = 4.0 * (2 * self.B) * 4096 * 4096 * 320                   # self-attn at T=4096, C=320 (5 x 64), plus kv=77 cross (small)
         t = kernel["avg_ms"] * 1e-3 if kernel["avg_ms"] else None
-        return {"kernel": "attn_fwd_kernel<bf16,64> (tcgen05), UNet self/cross attention at T=4096", "bound": "tensor",
+        return {"kernel": "attn_fwd_kernel<bf16,64> (tcgen05), UNet self-attention at T=4096 (5 heads x 64)", "bound": "tensor",
                 "achieved": flops / t / 1e12 if t else None, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": flops / t / 1e12 / peaks["bf16_tflops_sustained"] if t else None,
-                "note": "average over self (T_kv=4096) and cross (T_kv=77) calls; flops counted for the self-attention call",
+                "note": "self-attention calls at T = T_kv = 4096 only",
                 "avg_launch_us": t * 1e6 if t else None, "launches_timed": kernel["launches"], "traffic": None}
 
     def cpu_baseline(self):
