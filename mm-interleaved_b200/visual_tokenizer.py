@@ -527,12 +527,27 @@ CLIP_MEAN, CLIP_STD = [0.48145466, 0.4578275, 0.40821073], [0.26862954, 0.261302
 
 
 class VisualTokenizer(nn.Module):
-    def __init__(self, clip_config=None, perceiver_config=None, llm_hidden_size=5120, clip_normalize=True, grid_size=16):
+    def __init__(self, encoder_model_path=None, perceiver_config=None, llm_hidden_size=5120, clip_normalize=True,
+                 grid_size=16, clip_config=None):
+        """Reference constructor arguments (visual_tokenizer.py:12-19).  ``encoder_model_path`` is only consulted for
+        its ``config.json`` (vision_config fields); weights arrive through ``load_state_dict`` like in the reference's
+        ``load_model_weights`` (utils/misc.py:13-63).  ``clip_config`` (extension) overrides it."""
         super().__init__()
-        clip_config = clip_config or CLIPVisionConfigLite()
-        perceiver_config = dict(perceiver_config or dict(num_queries=64, hidden_size=768, encoder_hidden_size=1024,
-                                                         cross_attention_frequency=2, num_hidden_layers=12,
-                                                         num_attention_heads=12, qk_normalization=True))
+        if clip_config is None:
+            clip_config = CLIPVisionConfigLite()
+            cfg_file = None if encoder_model_path is None else __import__("os").path.join(str(encoder_model_path), "config.json")
+            if cfg_file and __import__("os").path.exists(cfg_file):
+                import json
+                raw = json.load(open(cfg_file))
+                raw = raw.get("vision_config", raw)
+                for k in ("hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads", "image_size",
+                          "patch_size", "layer_norm_eps"):
+                    if k in raw:
+                        setattr(clip_config, k, raw[k])
+        if perceiver_config is None:
+            perceiver_config = dict(num_queries=64, hidden_size=768, encoder_hidden_size=1024, cross_attention_frequency=2,
+                                    num_hidden_layers=12, num_attention_heads=12, qk_normalization=True)
+        perceiver_config = dict(perceiver_config) if not isinstance(perceiver_config, dict) else dict(perceiver_config)
         self.clip_normalize = clip_normalize
         self.encoder = CLIPVisionAdapterModel(clip_config)
         enc = perceiver_config["encoder_hidden_size"]
