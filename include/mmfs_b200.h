@@ -199,6 +199,18 @@ int mmfs_attn_forward(const void *q, const void *k, const void *v, void *out, co
                       long q_bs, long q_ts, long k_bs, long k_ts, long v_bs, long v_ts, long o_bs, long o_ts,
                       float scale, int causal, int past, int dtype, void *stream);
 
+/*
+ * 2-D convolution as an implicit GEMM on the tensor cores (tcgen05, TMA-shifted input boxes, no im2col buffer).
+ * Replaces the cuDNN convolutions diffusers' UNet issues in the denoise step (called from
+ * utils/monkey_patch/sd_unet_forward_monkey_patch.py:235-366; 3x3 stride 1/2 and 1x1, NHWC).
+ *   x (B,H,W,Cin) NHWC; w (Cout,KH,KW,Cin); out (B,Ho,Wo,Cout) NHWC; optional fused epilogue terms: bias (Cout),
+ *   add_bc (B,Cout) [the ResNet block's time-embedding projection], residual (like out).
+ * Requires bf16/f16, Cin % 64 == 0, Cout % 160 == 0, stride <= 2, output tileable by 8x16 (or 8x8 with even B) pixel
+ * patches: MMFS_EUNSUPPORTED otherwise (callers keep those few layers -- conv_in / conv_out -- on the library path).
+ */
+int mmfs_conv2d_nhwc(const void *x, const void *w, const void *bias, const void *add_bc, const void *residual, void *out,
+                     int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,3 +104,39 @@ def attention(q, k, v, key_mask=None, causal=True, past=0, scale=None, force_gen
         _lib.check(rc, "attention")
     launch_counter[0] += 1
     return out.view(B, Tq, H * hd)
+
+
+def conv2d_supported(x: torch.Tensor, weight: torch.Tensor, stride: int, padding: int) -> bool:
+    """Whether ``conv2d`` can take this layer (else the caller keeps it on cuDNN: conv_in / conv_out of the UNet)."""
+    if x.dtype not in (torch.bfloat16, torch.float16) or not x.is_cuda or x.dim() != 4:
+        return False
+    B, Cin, H, W = x.shape
+    Cout, _, KH, KW = weight.shape
+    Ho, Wo = (H + 2 * padding - KH) // stride + 1, (W + 2 * padding - KW) // stride + 1
+    tile = (Wo % 16 == 0 and Ho % 8 == 0) or (Wo == 8 and Ho == 8 and B % 2 == 0)
+    return Cin % 64 == 0 and Cout % 160 == 0 and stride in (1, 2) and tile
+
+
+def conv2d(x: torch.Tensor, weight_khwc: torch.Tensor, bias=None, stride: int = 1, padding: int = 0, add_bc=None,
+           residual=None) -> torch.Tensor:
+    """Implicit-GEMM convolution on the tensor cores (csrc/conv_igemm_sm100.cu).  ``x`` is a (B, Cin, H, W) tensor in
+    channels_last memory format (i.e. NHWC in memory); ``weight_khwc`` is the filter permuted to (Cout, KH, KW, Cin),
+    contiguous; returns (B, Cout, Ho, Wo) channels_last.  Optional fused epilogue: ``bias`` (Cout), ``add_bc``
+    (B, Cout) broadcast over pixels, ``residual`` (like the output, channels_last)."""
+    B, Cin, H, W = x.shape
+    Cout, KH, KW, _ = weight_khwc.shape
+    _require(x.is_contiguous(memory_format=torch.channels_last) and weight_khwc.is_contiguous(), "conv2d: x must be channels_last")
+    Ho, Wo = (H + 2 * padding - KH) // stride + 1, (W + 2 * padding - KW) // stride + 1
+    out = torch.empty((B, Cout, Ho, Wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    if residual is not None:
+        _require(residual.shape == out.shape and residual.is_contiguous(memory_format=torch.channels_last), "conv2d: residual layout")
+    if add_bc is not None:
+        add_bc = add_bc.contiguous()
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().mmfs_conv2d_nhwc(
+            x.data_ptr(), weight_khwc.data_ptr(), bias.data_ptr() if bias is not None else None,
+            add_bc.data_ptr() if add_bc is not None else None, residual.data_ptr() if residual is not None else None,
+            out.data_ptr(), B, H, W, Cin, Cout, KH, KW, stride, padding, _DTYPE_CODE[x.dtype], _stream())
+    _lib.check(rc, "conv2d")
+    launch_counter[0] += 1
+    return out
