@@ -564,7 +564,7 @@ class SdCfg4(Workload):
     def config(self):
         return {"workload": f"BASELINE cfg4: SD-2.1-base UNet (866 M params, random init) {self.STEPS}-step CFG denoise, latents "
                             f"({2 * self.B},4,64,64), ctx (77,1024), MMFSNet (13 blocks) on 1 context image; DDIM update as scheduler "
-                            "stand-in; convs / GroupNorm = cuDNN, attention + MMFS = this repo's kernels",
+                            "stand-in; 3x3/1x1 convs (tcgen05 implicit GEMM), GroupNorm+SiLU, attention, LayerNorm, MMFS = this repo's kernels; conv_in/conv_out + Linear GEMMs = cuDNN/cuBLAS",
                 "step_unit": "one 512^2 image (50 UNet evaluations at batch 2 for CFG)", "global_batch": self.B * self.world,
                 "parallelism": f"dp{self.world}", "l2": "192 MiB buffer written between timed steps"}
 

@@ -140,3 +140,26 @@ def conv2d(x: torch.Tensor, weight_khwc: torch.Tensor, bias=None, stride: int = 
     _lib.check(rc, "conv2d")
     launch_counter[0] += 1
     return out
+
+
+def group_norm_supported(x: torch.Tensor) -> bool:
+    if not x.is_cuda or x.dim() != 4 or x.dtype not in _DTYPE_CODE or x.dtype == torch.float64:
+        return False
+    vec = 16 // x.element_size()
+    return x.shape[1] % vec == 0 and x.shape[1] // vec <= 1024 and x.is_contiguous(memory_format=torch.channels_last)
+
+
+def group_norm_nhwc(x: torch.Tensor, groups: int, weight=None, bias=None, eps: float = 1e-5, silu: bool = False) -> torch.Tensor:
+    """``F.group_norm`` (+ ``F.silu`` when ``silu``) on a channels_last (B, C, H, W) tensor, result channels_last
+    (torch's CUDA group_norm returns NCHW, which costs a layout round trip around each convolution)."""
+    _require(group_norm_supported(x), "group_norm_nhwc: need a CUDA channels_last f32/f16/bf16 tensor with C % (16/size) == 0")
+    B, C, H, W = x.shape
+    y = torch.empty_like(x, memory_format=torch.channels_last)
+    stats = torch.empty((B, groups, 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().mmfs_groupnorm_nhwc(x.data_ptr(), weight.data_ptr() if weight is not None else None,
+                                            bias.data_ptr() if bias is not None else None, y.data_ptr(), stats.data_ptr(),
+                                            B, H * W, C, groups, float(eps), int(silu), _DTYPE_CODE[x.dtype], _stream())
+    _lib.check(rc, "group_norm_nhwc")
+    launch_counter[0] += 2
+    return y

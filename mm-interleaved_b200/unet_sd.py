@@ -13,8 +13,11 @@ here); the block-level formulas are checked against plain PyTorch statements in 
 
 B200 side: every self- and cross-attention runs in this repo's tcgen05 kernel (T in {4096, 1024, 256, 64},
 head size 64, kv = 77 for cross attention), the MMFS branch in the fused sampler (sd_mmfs.py), LayerNorms in the
-warp-per-row kernel; convolutions / GroupNorm are library calls (cuDNN, channels-last) -- the conv-as-GEMM tcgen05
-kernel of SURVEY.md section 7 step 5 is not built.
+warp-per-row kernel, and every 3x3 / 1x1 convolution with Cin % 64 == 0 and Cout % 160 == 0 (all but conv_in / conv_out
+when the model is bf16/f16 and channels-last) in the implicit-GEMM tcgen05 kernel (csrc/conv_igemm_sm100.cu) with the
+ResNet block's time-embedding add and residual add fused into its epilogue; GroupNorm(+SiLU) runs in an NHWC kernel
+(csrc/groupnorm_nhwc_sm100.cu) because torch's CUDA group_norm returns NCHW and would force a layout round trip
+around every convolution.
 """
 from __future__ import annotations
 
@@ -26,6 +29,36 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
+
+USE_CONV_KERNEL = True      # tests flip this to compare against the cuDNN path on the same weights
+
+
+def _gn(mod: nn.GroupNorm, x: torch.Tensor, silu: bool) -> torch.Tensor:
+    """``silu(mod(x))`` / ``mod(x)`` kept in NHWC by this repo's kernel when x is channels-last on the GPU."""
+    if USE_CONV_KERNEL and ops.group_norm_supported(x):
+        return ops.group_norm_nhwc(x, mod.num_groups, mod.weight, mod.bias, mod.eps, silu=silu)
+    h = mod(x)
+    return F.silu(h) if silu else h
+
+
+def _conv(mod: nn.Conv2d, x: torch.Tensor, add_bc: Optional[torch.Tensor] = None,
+          residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``mod(x) [+ add_bc[:, :, None, None]] [+ residual]`` -- on the tcgen05 implicit-GEMM kernel when the layer
+    qualifies (ops.conv2d_supported), else on the library convolution."""
+    stride, pad = mod.stride[0], mod.padding[0]
+    if USE_CONV_KERNEL and x.is_contiguous(memory_format=torch.channels_last) and ops.conv2d_supported(x, mod.weight, stride, pad):
+        cache = getattr(mod, "_w_khwc", None)
+        if cache is None or cache[0] != (mod.weight.data_ptr(), mod.weight._version, mod.weight.dtype):
+            cache = ((mod.weight.data_ptr(), mod.weight._version, mod.weight.dtype),
+                     mod.weight.detach().permute(0, 2, 3, 1).contiguous())
+            mod._w_khwc = cache
+        if residual is not None and not residual.is_contiguous(memory_format=torch.channels_last):
+            residual = residual.contiguous(memory_format=torch.channels_last)
+        return ops.conv2d(x, cache[1], mod.bias, stride, pad, add_bc=add_bc, residual=residual)
+    h = mod(x)
+    if add_bc is not None:
+        h = h + add_bc[:, :, None, None]
+    return h if residual is None else h + residual
 
 
 def timestep_embedding(timesteps: torch.Tensor, dim: int, max_period: int = 10000) -> torch.Tensor:
@@ -57,10 +90,9 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else None
 
     def forward(self, x, temb):
-        h = self.conv1(F.silu(self.norm1(x)))
-        h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
-        h = self.conv2(F.silu(self.norm2(h)))
-        return (x if self.conv_shortcut is None else self.conv_shortcut(x)) + h
+        h = _conv(self.conv1, _gn(self.norm1, x, True), add_bc=self.time_emb_proj(F.silu(temb)))
+        skip = x if self.conv_shortcut is None else _conv(self.conv_shortcut, x)
+        return _conv(self.conv2, _gn(self.norm2, h, True), residual=skip)
 
 
 class Attention(nn.Module):
@@ -135,7 +167,7 @@ class Transformer2DModel(nn.Module):
 
     def forward(self, x, context):
         B, C, H, W = x.shape
-        h = self.norm(x).permute(0, 2, 3, 1).reshape(B, H * W, C)
+        h = _gn(self.norm, x, False).permute(0, 2, 3, 1).reshape(B, H * W, C)
         h = self.proj_in(h)
         for blk in self.transformer_blocks:
             h = blk(h, context)
@@ -149,7 +181,7 @@ class Downsample2D(nn.Module):
         self.conv = nn.Conv2d(channels, channels, 3, stride=2, padding=1)
 
     def forward(self, x):
-        return self.conv(x)
+        return _conv(self.conv, x)
 
 
 class Upsample2D(nn.Module):
@@ -158,7 +190,7 @@ class Upsample2D(nn.Module):
         self.conv = nn.Conv2d(channels, channels, 3, padding=1)
 
     def forward(self, x):
-        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+        return _conv(self.conv, F.interpolate(x, scale_factor=2.0, mode="nearest"))
 
 
 class DownBlock(nn.Module):
@@ -263,7 +295,7 @@ class UNet2DConditionModel(nn.Module):
         res = list(res)
         for blk in self.up_blocks:
             sample = blk(sample, res, emb, encoder_hidden_states)
-        return self.conv_out(F.silu(self.conv_norm_out(sample)))
+        return self.conv_out(_gn(self.conv_norm_out, sample, True))
 
 
 @torch.no_grad()

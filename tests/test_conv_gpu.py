@@ -52,3 +52,23 @@ def test_unsupported_layers_are_reported():
     x = torch.randn((2, 4, 64, 64), device=DEV, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
     assert not ops.conv2d_supported(x, torch.empty(320, 4, 3, 3), 1, 1)          # conv_in: Cin = 4
     assert not ops.conv2d_supported(torch.empty((2, 320, 64, 64), device=DEV), torch.empty(320, 320, 3, 3), 1, 1)   # fp32
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1.6e-2), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("shape,silu", [((2, 320, 32, 32), True), ((3, 64, 16, 16), False), ((2, 960, 8, 8), True),
+                                        ((1, 2560, 8, 8), True), ((2, 1920, 16, 16), False)])
+def test_group_norm_nhwc_matches_torch(shape, silu, dtype, tol):
+    """NHWC GroupNorm(32)(+SiLU) vs F.group_norm in fp32 on the same rounded inputs; |err| <= tol * max(1, |ref|)."""
+    from mm_interleaved_b200 import ops
+    g = torch.Generator().manual_seed(shape[1])
+    x = (torch.randn(shape, generator=g) * 1.5 + 0.7).to(dtype)
+    w = (1 + 0.2 * torch.randn(shape[1], generator=g)).to(dtype)
+    b = (0.2 * torch.randn(shape[1], generator=g)).to(dtype)
+    xd = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    out = ops.group_norm_nhwc(xd, 32, w.to(DEV), b.to(DEV), 1e-5, silu=silu)
+    ref = torch.nn.functional.group_norm(x.float(), 32, w.float(), b.float(), 1e-5)
+    if silu:
+        ref = torch.nn.functional.silu(ref)
+    assert out.is_contiguous(memory_format=torch.channels_last) and out.dtype == dtype
+    err = (out.float().cpu() - ref).abs()
+    assert (err <= tol * ref.abs().clamp_min(1.0)).all(), err.max().item()
