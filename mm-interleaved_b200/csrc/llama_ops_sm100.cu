@@ -61,6 +61,57 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const T *__restrict__ x, c
         yr[i] = from_op<T>(to_op(w[i]) * rnd<T>(to_op(xr[i]) * r));
 }
 
+// Single-pass variant: 128 threads per row, the row stays in registers (up to kRmsChunks 16-byte vectors per thread:
+// 8192 bf16 / 4096 fp32 columns), one shared-memory exchange between the four warps.  HBM traffic = read + write once.
+constexpr int kRmsChunks = 8;
+constexpr int kRmsThreads = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(kRmsThreads) rmsnorm_reg_kernel(const T *__restrict__ x, const T *__restrict__ w,
+                                                                  T *__restrict__ y, int cols, float eps) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    __shared__ float s_red[kRmsThreads / 32];
+    const size_t row = blockIdx.x;
+    const T *xr = x + row * cols;
+    T *yr = y + row * cols;
+    const int nvec = cols / VEC;                      // host: cols % VEC == 0, nvec <= kRmsThreads * kRmsChunks
+    uint4 v[kRmsChunks];
+#pragma unroll
+    for (int c = 0; c < kRmsChunks; ++c) {
+        const int i = threadIdx.x + c * kRmsThreads;
+        if (i < nvec) v[c] = ldg_nc_v4(xr + i * VEC);
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < kRmsChunks; ++c)
+        if (threadIdx.x + c * kRmsThreads < nvec) {
+            float f[VEC];
+            Vec16<T>::unpack(v[c], f);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) ss = fmaf(f[k], f[k], ss);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRmsThreads / 32; ++i) tot += s_red[i];
+    const float r = rsqrtf(tot / (float)cols + eps);
+#pragma unroll
+    for (int c = 0; c < kRmsChunks; ++c) {
+        const int i = threadIdx.x + c * kRmsThreads;
+        if (i < nvec) {
+            float f[VEC], g[VEC], o[VEC];
+            Vec16<T>::unpack(v[c], f);
+            Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(w + i * VEC), g);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) o[k] = g[k] * rnd<T>(f[k] * r);
+            stg_v4(yr + i * VEC, Vec16<T>::pack(o));
+        }
+    }
+}
+
 // ---- LayerNorm (biased variance, fp32 statistics) ------------------------------------------------------
 // Warp per row: the row lives in registers (16-byte vector loads), mean and centred variance are two warp
 // reductions, one pass over HBM.  Rows of up to 32 * VEC * kLnChunks elements (2048 bf16 / 1024 fp32) take this
@@ -141,50 +192,79 @@ __global__ void __launch_bounds__(256) rope_qk_kernel(T *__restrict__ q, T *__re
                                                        const float *__restrict__ sin_t, const int64_t *__restrict__ pos,
                                                        long n_tok, int H, int hd, int q_stride, int k_stride, int pos_per_batch,
                                                        int T_len) {
-    // one thread per (token, head, q-or-k, chunk of VEC rotation pairs): two 16-byte loads (x1 | x2 halves),
-    // two 16-byte stores; cos/sin rows are fp32 and L1/L2 resident (one row per token)
+    // one CTA per token (grid-stride), one thread per (q-or-k, head, chunk of VEC rotation pairs): two 16-byte loads
+    // (x1 | x2 halves), two 16-byte stores; the token's cos/sin row is fp32 and read through L1 by every head.
+    // All index math is 32-bit and per token, so the kernel is pure load/store.
     constexpr int VEC = 16 / (int)sizeof(T);
     const int half = hd >> 1;
     const int chunks = half / VEC;
-    const long total = n_tok * H * 2 * chunks;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % chunks);
-        long r = idx / chunks;
-        const int which = (int)(r & 1); r >>= 1;
-        const int h = (int)(r % H);
-        const long tok = r / H;
+    const int per_tok = 2 * H * chunks;
+    for (long tok = blockIdx.x; tok < n_tok; tok += gridDim.x) {
         const long p = pos[pos_per_batch ? tok : (tok % T_len)];
-        T *x = (which ? k + tok * k_stride : q + tok * q_stride) + (size_t)h * hd + c * VEC;
-        float x1[VEC], x2[VEC], o1[VEC], o2[VEC];
-        Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(x), x1);
-        Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(x + half), x2);
-        const float *cp = cos_t + p * hd + c * VEC, *sp = sin_t + p * hd + c * VEC;
+        const float *cp = cos_t + p * hd, *sp = sin_t + p * hd;
+        T *qt = q + tok * q_stride, *kt = k + tok * k_stride;
+        for (int it = threadIdx.x; it < per_tok; it += blockDim.x) {
+            const int c = it % chunks;
+            const int hh = it / chunks;                 // 0 .. 2H-1: q heads then k heads
+            T *x = (hh >= H ? kt + (size_t)(hh - H) * hd : qt + (size_t)hh * hd) + c * VEC;
+            float x1[VEC], x2[VEC], o1[VEC], o2[VEC], cs[VEC], sn[VEC];
+            Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(x), x1);
+            Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(x + half), x2);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const float cs = rnd<T>(cp[i]), sn = rnd<T>(sp[i]);          // tables cast to x.dtype (:141-144)
-            o1[i] = rnd<T>(x1[i] * cs) + rnd<T>(-x2[i] * sn);
-            o2[i] = rnd<T>(x2[i] * cs) + rnd<T>(x1[i] * sn);
+            for (int i = 0; i < VEC; i += 4) {
+                const float4 a = *reinterpret_cast<const float4 *>(cp + c * VEC + i);
+                const float4 b = *reinterpret_cast<const float4 *>(sp + c * VEC + i);
+                cs[i] = a.x; cs[i + 1] = a.y; cs[i + 2] = a.z; cs[i + 3] = a.w;
+                sn[i] = b.x; sn[i + 1] = b.y; sn[i + 2] = b.z; sn[i + 3] = b.w;
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float c_ = rnd<T>(cs[i]), s_ = rnd<T>(sn[i]);      // tables cast to x.dtype (:141-144)
+                o1[i] = rnd<T>(x1[i] * c_) + rnd<T>(-x2[i] * s_);
+                o2[i] = rnd<T>(x2[i] * c_) + rnd<T>(x1[i] * s_);
+            }
+            *reinterpret_cast<uint4 *>(x) = Vec16<T>::pack(o1);
+            *reinterpret_cast<uint4 *>(x + half) = Vec16<T>::pack(o2);
         }
-        *reinterpret_cast<uint4 *>(x) = Vec16<T>::pack(o1);
-        *reinterpret_cast<uint4 *>(x + half) = Vec16<T>::pack(o2);
     }
 }
 
 // ---- SwiGLU: out = silu(gate) * up, gate|up stored as one (rows, 2*I) GEMM output -------------------
+// silu in fp32: exact expf / division for fp32 tensors; ex2.approx + rcp.approx for 16-bit tensors, whose result is
+// rounded to 8 / 11 significand bits right after (relative error of the fast path ~2^-21).
+template <typename T> __device__ __forceinline__ float silu_op(float g) { return __fdividef(g, 1.f + __expf(-g)); }
+template <> __device__ __forceinline__ float silu_op<float>(float g) { return g / (1.f + expf(-g)); }
+
 template <typename T>
 __global__ void __launch_bounds__(256) swiglu_kernel(const T *__restrict__ gu, T *__restrict__ out, long rows, int I) {
+    // CTA per row (grid-stride): no 64-bit index division, two independent (gate, up) vector pairs in flight per thread
     constexpr int VEC = 16 / (int)sizeof(T);
     const int nvec = I / VEC;
-    const long total = rows * nvec;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const long r = idx / nvec;
-        const int c = (int)(idx % nvec) * VEC;
-        float g[VEC], u[VEC], o[VEC];
-        Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(gu + r * 2 * I + c), g);
-        Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(gu + r * 2 * I + I + c), u);
+    for (long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const T *g_row = gu + r * 2 * I, *u_row = g_row + I;
+        T *o_row = out + r * I;
+        int i = threadIdx.x;
+        for (; i + (int)blockDim.x < nvec; i += 2 * blockDim.x) {
+            const int j = i + blockDim.x;
+            const uint4 g0 = ldg_nc_v4(g_row + i * VEC), u0 = ldg_nc_v4(u_row + i * VEC);
+            const uint4 g1 = ldg_nc_v4(g_row + j * VEC), u1 = ldg_nc_v4(u_row + j * VEC);
+            float g[VEC], u[VEC], o[VEC];
+            Vec16<T>::unpack(g0, g); Vec16<T>::unpack(u0, u);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) o[k] = rnd<T>(g[k] / (1.f + expf(-g[k]))) * u[k];   // act_fn(gate) is a tensor in T
-        *reinterpret_cast<uint4 *>(out + r * I + c) = Vec16<T>::pack(o);
+            for (int k = 0; k < VEC; ++k) o[k] = rnd<T>(silu_op<T>(g[k])) * u[k];   // act_fn(gate) is a tensor in T
+            stg_v4(o_row + i * VEC, Vec16<T>::pack(o));
+            Vec16<T>::unpack(g1, g); Vec16<T>::unpack(u1, u);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) o[k] = rnd<T>(silu_op<T>(g[k])) * u[k];
+            stg_v4(o_row + j * VEC, Vec16<T>::pack(o));
+        }
+        if (i < nvec) {
+            float g[VEC], u[VEC], o[VEC];
+            Vec16<T>::unpack(ldg_nc_v4(g_row + i * VEC), g); Vec16<T>::unpack(ldg_nc_v4(u_row + i * VEC), u);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) o[k] = rnd<T>(silu_op<T>(g[k])) * u[k];
+            stg_v4(o_row + i * VEC, Vec16<T>::pack(o));
+        }
     }
 }
 
@@ -194,7 +274,10 @@ static int launch_all(int which, const void *a, const void *b, const void *c, vo
     (void)i5;
     switch (which) {
         case 0:   // rmsnorm: a=x b=w d=y n0=rows i0=cols
-            rmsnorm_kernel<T><<<(unsigned)n0, 256, 0, st>>>((const T *)a, (const T *)b, (T *)d, i0, eps);
+            if (i0 % (16 / (int)sizeof(T)) == 0 && i0 / (16 / (int)sizeof(T)) <= kRmsThreads * kRmsChunks)
+                rmsnorm_reg_kernel<T><<<(unsigned)n0, kRmsThreads, 0, st>>>((const T *)a, (const T *)b, (T *)d, i0, eps);
+            else
+                rmsnorm_kernel<T><<<(unsigned)n0, 256, 0, st>>>((const T *)a, (const T *)b, (T *)d, i0, eps);
             break;
         case 1: { // layernorm: a=x b=w c=bias d=y
             constexpr int VEC = 16 / (int)sizeof(T);
@@ -207,16 +290,18 @@ static int launch_all(int which, const void *a, const void *b, const void *c, vo
             break;
         }
         case 2: { // rope: d=q (in place), a=k (in place, cast away const), e=cos f=sin c=pos; n0=tokens i0=H i1=hd i2=q_stride i3=k_stride i4=pos_per_batch i5=T
-            const long total = n0 * i0 * 2 * ((i1 / 2) / (16 / (int)sizeof(T)));
-            const int grid = (int)((total + 255) / 256 < 148L * 16 ? (total + 255) / 256 : 148L * 16);
-            rope_qk_kernel<T><<<grid, 256, 0, st>>>((T *)d, (T *)const_cast<void *>(a), (const float *)e, (const float *)f,
+            const int per_tok = i0 * 2 * ((i1 / 2) / (16 / (int)sizeof(T)));
+            const int threads = per_tok >= 256 ? 256 : ((per_tok + 31) / 32) * 32;
+            const int grid = (int)(n0 < 148L * 32 ? n0 : 148L * 32);
+            rope_qk_kernel<T><<<grid, threads, 0, st>>>((T *)d, (T *)const_cast<void *>(a), (const float *)e, (const float *)f,
                                                      (const int64_t *)c, n0, i0, i1, i2, i3, i4, i5);
             break;
         }
         case 3: { // swiglu: a=gate_up d=out n0=rows i0=I
-            const long total = n0 * (i0 / (16 / (int)sizeof(T)));
-            const int grid = (int)((total + 255) / 256 < 148L * 16 ? (total + 255) / 256 : 148L * 16);
-            swiglu_kernel<T><<<grid, 256, 0, st>>>((const T *)a, (T *)d, n0, i0);
+            const int nvec = i0 / (16 / (int)sizeof(T));
+            const int threads = nvec >= 512 ? 256 : (nvec >= 64 ? 64 : 32);
+            const int grid = (int)(n0 < 148L * 64 ? n0 : 148L * 64);
+            swiglu_kernel<T><<<grid, threads, 0, st>>>((const T *)a, (T *)d, n0, i0);
             break;
         }
     }

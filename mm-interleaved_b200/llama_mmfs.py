@@ -88,6 +88,17 @@ class _CatWeight:
         return self.weight
 
 
+def _addmm_residual(residual, x, weight, inplace):
+    """residual + x @ weight^T as one GEMM with the residual as the beta = 1 accumulator.  ``torch.addmm`` out of
+    place first copies the residual into the result (a D2D memcpy of the whole stream per call); in place skips it."""
+    r2 = residual.view(-1, residual.shape[-1])
+    x2 = x.reshape(-1, x.shape[-1])
+    if inplace:
+        r2.addmm_(x2, weight.t())
+        return residual
+    return torch.addmm(r2, x2, weight.t()).view_as(residual)
+
+
 class LlamaMLP(nn.Module):
     def __init__(self, hidden_size: int, intermediate_size: int, hidden_act: str):
         super().__init__()
@@ -98,13 +109,13 @@ class LlamaMLP(nn.Module):
         self.up_proj = nn.Linear(hidden_size, intermediate_size, bias=False)
         self._gate_up = _CatWeight(self.gate_proj, self.up_proj)
 
-    def forward(self, x, residual=None):
+    def forward(self, x, residual=None, inplace=False):
+        """``inplace``: accumulate into ``residual``'s storage (beta = 1 GEMM epilogue, no copy of the stream)."""
         gu = F.linear(x, self._gate_up.get())                 # [gate | up] in one GEMM
         act = ops.swiglu(gu)
         if residual is None:
             return self.down_proj(act)
-        out = torch.addmm(residual.reshape(-1, residual.shape[-1]), act.reshape(-1, act.shape[-1]), self.down_proj.weight.t())
-        return out.view_as(residual)
+        return _addmm_residual(residual, act, self.down_proj.weight, inplace)
 
 
 class LlamaAttention(nn.Module):
@@ -131,7 +142,7 @@ class LlamaAttention(nn.Module):
         return self._rope[2], self._rope[3]
 
     def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,
-                output_attentions=False, use_cache=False, residual=None):
+                output_attentions=False, use_cache=False, residual=None, inplace=False):
         """``attention_mask``: (B, T_kv) key-padding mask, 1 = attend (what LlamaModel.forward receives,
         modeling_llama_mmfs.py:625) or None.  Causality is implicit (decoder).  Returns
         (attn_output [+ residual], None, present_key_value) like the reference (:217-280); the cache
@@ -158,11 +169,7 @@ class LlamaAttention(nn.Module):
             else:
                 key_mask = attention_mask
         ctx = ops.attention(q, k, v, key_mask=key_mask, causal=True, past=past)       # (B, T, H*hd)
-        if residual is None:
-            out = self.o_proj(ctx)
-        else:
-            out = torch.addmm(residual.reshape(-1, self.hidden_size), ctx.view(-1, self.hidden_size),
-                              self.o_proj.weight.t()).view_as(residual)
+        out = self.o_proj(ctx) if residual is None else _addmm_residual(residual, ctx, self.o_proj.weight, inplace)
         return out, None, present
 
 
@@ -200,7 +207,16 @@ class LlamaMMFSAttention(nn.Module):
             self._geom_cache[rkey] = torch.full((1, len_q, 1, 2), 0.5, dtype=torch.float32, device=device)
         return self._geom_cache[key] + (self._geom_cache[rkey],)
 
-    def forward(self, hidden_states, vision_hidden_states=None, cross_attention_mask=None, residual=None):
+    def _gated_output(self):
+        """``output_proj`` pre-multiplied by tanh(gate) (:334 applies the gate to the block output), inference only."""
+        w, b, g = self.attn.output_proj.weight, self.attn.output_proj.bias, self.gate
+        key = (w.data_ptr(), w._version, b._version, g._version, w.dtype, w.device)
+        if getattr(self, "_gated", None) is None or self._gated[0] != key:
+            t = g.detach().float().tanh()
+            self._gated = (key, (w.detach().float() * t).to(w.dtype), (b.detach().float() * t).to(b.dtype))
+        return self._gated[1], self._gated[2]
+
+    def forward(self, hidden_states, vision_hidden_states=None, cross_attention_mask=None, residual=None, inplace=False):
         h = self.norm1(hidden_states)
         vkey = (vision_hidden_states.data_ptr(), tuple(vision_hidden_states.shape), vision_hidden_states._version,
                 self.norm2.weight._version)
@@ -209,6 +225,14 @@ class LlamaMMFSAttention(nn.Module):
         v = self._vision_cache[1]
         _, n_img, hw, _ = v.shape
         shapes, starts, ref = self._geometry(h.device, n_img, hw, h.shape[1])
+        if not torch.is_grad_enabled():
+            gw, gb = self._gated_output()
+            out = self.attn(query=h, reference_points=ref, input_flatten=v, input_spatial_shapes=shapes,
+                            input_level_start_index=starts, input_padding_mask=None, attention_mask=cross_attention_mask,
+                            output_weight=gw, output_bias=gb)
+            if residual is None:
+                return out
+            return residual.add_(out) if inplace else residual + out
         out = self.attn(query=h, reference_points=ref, input_flatten=v, input_spatial_shapes=shapes,
                         input_level_start_index=starts, input_padding_mask=None, attention_mask=cross_attention_mask)
         gate = self.gate.tanh().to(out.dtype)
@@ -229,17 +253,21 @@ class LlamaDecoderLayer(nn.Module):
         self.post_attention_layernorm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
 
     def forward(self, hidden_states, vision_hidden_states, cross_attention_mask, attention_mask=None,
-                position_ids=None, past_key_value=None, output_attentions=False, use_cache=False):
+                position_ids=None, past_key_value=None, output_attentions=False, use_cache=False, inplace=False):
         # norm -> self-attn -> (+) -> [MMFS cross-attn -> (+)] -> norm -> SwiGLU -> (+)   (:418-441)
+        # ``inplace`` (extension, inference): the residual stream is updated in its own storage -- the caller
+        # guarantees ``hidden_states`` is a private contiguous buffer (LlamaModel.forward clones the embeddings once).
         residual = hidden_states.contiguous()
+        inplace = inplace and not torch.is_grad_enabled()
         h = self.input_layernorm(residual)
         hidden_states, _, present = self.self_attn(h, attention_mask=attention_mask, position_ids=position_ids,
-                                                   past_key_value=past_key_value, use_cache=use_cache, residual=residual)
+                                                   past_key_value=past_key_value, use_cache=use_cache, residual=residual,
+                                                   inplace=inplace)
         if self.llama_cross_attn is not None and vision_hidden_states is not None:
             hidden_states = self.llama_cross_attn(hidden_states, vision_hidden_states, cross_attention_mask,
-                                                  residual=hidden_states)
+                                                  residual=hidden_states, inplace=inplace)
         h = self.post_attention_layernorm(hidden_states)
-        hidden_states = self.mlp(h, residual=hidden_states)
+        hidden_states = self.mlp(h, residual=hidden_states, inplace=inplace)
         outputs = (hidden_states,)
         if use_cache:
             outputs += (present,)
@@ -294,6 +322,9 @@ class LlamaModel(nn.Module):
             key_mask = attention_mask.to(torch.uint8)
 
         hidden_states = inputs_embeds
+        inplace = not torch.is_grad_enabled() and not output_hidden_states
+        if inplace:                      # one private copy of the stream; every layer then accumulates into it
+            hidden_states = hidden_states.clone(memory_format=torch.contiguous_format)
         all_hidden = () if output_hidden_states else None
         next_cache = () if use_cache else None
         for idx, layer in enumerate(self.layers):
@@ -302,7 +333,7 @@ class LlamaModel(nn.Module):
             outs = layer(hidden_states, vision_hidden_states, cross_attention_mask, attention_mask=key_mask,
                          position_ids=position_ids,
                          past_key_value=past_key_values[idx] if past_key_values is not None else None,
-                         use_cache=use_cache)
+                         use_cache=use_cache, inplace=inplace)
             hidden_states = outs[0]
             if use_cache:
                 next_cache += (outs[1],)

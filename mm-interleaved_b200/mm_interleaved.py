@@ -12,6 +12,7 @@ from __future__ import annotations
 from typing import List, Optional, Sequence
 
 import torch
+import torch.nn.functional as F
 from torch import nn
 
 from .llama_mmfs import LlamaMMFSConfig, LlamaModel
@@ -80,10 +81,26 @@ class TextHead(nn.Module):
         self.head = nn.Linear(hidden_size, vocab_size, bias=False)
         self.head_new = nn.Linear(hidden_size, vocab_size - orig_vocab_size, bias=False)
 
+    _PAD = 128   # a vocabulary of 32002+ rows is not a multiple of 8: cuBLAS drops to an unaligned legacy kernel (5x slower)
+
+    def _fused_weight(self):
+        """head + head_new folded into one matrix, rows zero-padded to a multiple of 128 (inference only)."""
+        key = tuple((w.data_ptr(), w._version, w.dtype, w.device) for w in (self.head.weight, self.head_new.weight))
+        if getattr(self, "_fused", None) is None or self._fused[0] != key:
+            V, C = self.head.weight.shape
+            Vp = (V + self._PAD - 1) // self._PAD * self._PAD
+            w = self.head.weight.new_zeros((Vp, C))
+            w[:V] = self.head.weight.detach()
+            w[self.orig_txt_vocab_size:V] += self.head_new.weight.detach()
+            self._fused = (key, w)
+        return self._fused[1]
+
     def forward(self, hidden_states):
-        logits = self.head(hidden_states)
-        logits[..., self.orig_txt_vocab_size:] += self.head_new(hidden_states)
-        return logits
+        if torch.is_grad_enabled() and (self.head.weight.requires_grad or self.head_new.weight.requires_grad):
+            logits = self.head(hidden_states)
+            logits[..., self.orig_txt_vocab_size:] += self.head_new(hidden_states)
+            return logits
+        return F.linear(hidden_states, self._fused_weight())[..., :self.head.weight.shape[0]]
 
 
 class InterleavedForward(nn.Module):

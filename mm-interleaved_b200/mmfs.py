@@ -32,8 +32,26 @@ from . import sampler as _sampler
 _FAST_HEAD_DIMS = (32, 64, 128)
 
 
+_RELPOS_CACHE = {}
+
+
 def relative_image_index(attention_mask: torch.Tensor, len_q: int) -> torch.Tensor:
-    """uint8 (N, n_img, 1|Lq): newest visible image -> 1, older -> 2.., masked -> 0 (mmfs.py:154-163)."""
+    """uint8 (N, n_img, 1|Lq): newest visible image -> 1, older -> 2.., masked -> 0 (mmfs.py:154-163).
+    Every MMFS layer of a forward receives the same mask tensor, so the last result is kept (keyed on the
+    tensor's storage + version) instead of being recomputed per layer."""
+    key = (attention_mask.data_ptr(), attention_mask._version, tuple(attention_mask.shape), attention_mask.dtype,
+           attention_mask.device, len_q)
+    hit = _RELPOS_CACHE.get("last")
+    if hit is not None and hit[0] == key and hit[1]() is attention_mask:
+        return hit[2]
+    rel = _relative_image_index(attention_mask, len_q)
+    if not torch.is_grad_enabled() or not attention_mask.requires_grad:
+        import weakref
+        _RELPOS_CACHE["last"] = (key, weakref.ref(attention_mask), rel)
+    return rel
+
+
+def _relative_image_index(attention_mask: torch.Tensor, len_q: int) -> torch.Tensor:
     m = attention_mask.long()
     tot = m.sum(dim=-1, keepdim=True)
     rel = (tot + 1 - m.cumsum(dim=-1)) * m
