@@ -57,6 +57,25 @@ __device__ __forceinline__ float fast_exp2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// packed fp32 pairs (Blackwell fma.rn.f32x2 / add.rn.f32x2: two lanes per issue slot)
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float &a, float &b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 // two back-to-back 32-column TMEM loads, one wait
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
     uint32_t r[64];
@@ -201,6 +220,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // rescaled consistently, p <= 2^8 fits bf16/f16) and saves most TMEM round trips on O.
         float m_ref = -INFINITY, l_run = 0.f;
         const int causal_limit = p.causal ? (p.past + q_abs) : 0x7fffffff;   // last visible key index
+        const int warp_causal_limit = p.causal ? (p.past + q0 + quarter * 32) : 0x7fffffff;   // ... of the warp's first row
         uint8_t *p_row = sP + row * 128;
 
         for (int j = 0; j < n_tiles; ++j) {
@@ -215,36 +235,49 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             }
             bar_wait(s_full + s, (j >> 1) & 1);
             tc_fence_after();
-            const bool need_mask = (k0 + kBN - 1 > causal_limit) || (k0 + kBN > p.Tkv) || (p.key_mask != nullptr);
+            // warp-uniform on purpose (lane 0 of the warp has the tightest causal limit): a per-lane condition makes
+            // the compiler predicate the whole mask code into the hot loop (2.5x the instructions of an unmasked tile)
+            const bool need_mask = (k0 + kBN - 1 > warp_causal_limit) || (k0 + kBN > p.Tkv) || (p.key_mask != nullptr);
 
             float sc[kBN];
             tmem_ld64(tmem_s0 + (uint32_t)s * kBN + lane_sel, sc);
-            float m_tile = -INFINITY;
+            if (need_mask) {
 #pragma unroll
-            for (int i = 0; i < kBN; ++i) {
-                if (need_mask) {
+                for (int i = 0; i < kBN; ++i) {
                     const int kj = k0 + i;
                     const bool ok = (kj <= causal_limit) && (kj < p.Tkv) && (p.key_mask == nullptr || s_kmask[s * kBN + i]);
                     sc[i] = ok ? sc[i] : -INFINITY;
                 }
-                m_tile = fmaxf(m_tile, sc[i]);
             }
+            float m_tile = fmaxf(sc[0], sc[1]);
+#pragma unroll
+            for (int i = 2; i < kBN; i += 2) m_tile = fmaxf(m_tile, fmaxf(sc[i], sc[i + 1]));   // FMNMX3
             const float m_cand = fmaxf(m_ref, m_tile);
             const bool grow = (m_cand > m_ref) && (m_ref == -INFINITY || (m_cand - m_ref) * p.scale_log2e > kRescaleThreshold);
             const float alpha = grow ? ((m_ref == -INFINITY) ? 0.f : fast_exp2((m_ref - m_cand) * p.scale_log2e)) : 1.f;
             if (grow) m_ref = m_cand;
             const float m_scaled = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2e;
 
-            // P = exp2(S * scale_log2e - m_ref), row sum, pack to 16 bit
-            float l_tile = 0.f;
+            // P = exp2(S * scale_log2e - m_ref), row sum, pack to 16 bit.  The affine map and the row sum use the
+            // packed fp32 pipe (fma.rn.f32x2 / add.rn.f32x2: one issue slot per two elements); exp2 is MUFU.
+            const uint64_t sc2 = pack_f32x2(p.scale_log2e, p.scale_log2e), neg_m2 = pack_f32x2(-m_scaled, -m_scaled);
+            uint64_t l2a = 0ull, l2b = 0ull;        // two independent packed accumulators (bit pattern of +0.f, +0.f)
             uint32_t pk[kBN / 2];
 #pragma unroll
-            for (int i = 0; i < kBN; i += 2) {
-                const float e0 = fast_exp2(sc[i] * p.scale_log2e - m_scaled);       // masked: exp2(-inf) = 0
-                const float e1 = fast_exp2(sc[i + 1] * p.scale_log2e - m_scaled);
-                l_tile += e0 + e1;
+            for (int i = 0; i < kBN; i += 4) {
+                float x0, x1, x2, x3;
+                unpack_f32x2(fma_f32x2(pack_f32x2(sc[i], sc[i + 1]), sc2, neg_m2), x0, x1);   // masked: exp2(-inf) = 0
+                unpack_f32x2(fma_f32x2(pack_f32x2(sc[i + 2], sc[i + 3]), sc2, neg_m2), x2, x3);
+                const float e0 = fast_exp2(x0), e1 = fast_exp2(x1), e2 = fast_exp2(x2), e3 = fast_exp2(x3);
+                l2a = add_f32x2(l2a, pack_f32x2(e0, e1));
+                l2b = add_f32x2(l2b, pack_f32x2(e2, e3));
                 pk[i >> 1] = pack2<T>(e0, e1);
+                pk[(i >> 1) + 1] = pack2<T>(e2, e3);
             }
+            float la, lb, lc, ld;
+            unpack_f32x2(l2a, la, lb);
+            unpack_f32x2(l2b, lc, ld);
+            const float l_tile = (la + lb) + (lc + ld);
             l_run = l_run * alpha + l_tile;
 
             // the previous P V must have retired before P is overwritten / O is rescaled
