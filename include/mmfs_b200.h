@@ -173,6 +173,9 @@ int mmfs_rope_qk(void *q, void *k, const float *cos_table, const float *sin_tabl
                  long n_tokens, int T_len, int H, int hd, int q_stride, int k_stride, int pos_per_batch,
                  int dtype, void *stream);
 int mmfs_swiglu(const void *gate_up, void *out, long rows, int inter, int dtype, void *stream);
+/* GEGLU of the SD-UNet feed-forward (diffusers GEGLU: hidden, gate = proj(x).chunk(2); hidden * gelu(gate), exact erf
+ * GELU), on one (rows, 2*inter) buffer holding [value | gate]. */
+int mmfs_geglu(const void *value_gate, void *out, long rows, int inter, int dtype, void *stream);
 
 /*
  * softmax(q k^T * scale + mask) v for decode (q_len = 1 over a KV cache) and small / odd shapes;

@@ -37,6 +37,7 @@ SIGNATURES = {
     "mmfs_layernorm": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P]),
     "mmfs_rope_qk": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _P]),
     "mmfs_swiglu": (_I, [_P, _P, _L, _I, _I, _P]),
+    "mmfs_geglu": (_I, [_P, _P, _L, _I, _I, _P]),
     "mmfs_attn_generic": (_I, [_P] * 5 + [_I] * 5 + [_L] * 8 + [_F, _I, _I, _I, _P]),
     "mmfs_groupnorm_nhwc": (_I, [_P] * 5 + [_I] * 4 + [_F, _I, _I, _P]),
     "mmfs_conv2d_nhwc": (_I, [_P] * 6 + [_I] * 10 + [_P]),

@@ -15,21 +15,24 @@
 //     thread; accumulators live in TMEM: two S buffers (2 x 128 columns) so that S_{j+1} is
 //     computed while the softmax of S_j runs, plus the O accumulator (hd columns);
 //   * 4 softmax warps own one TMEM lane (= one query row) per thread: tcgen05.ld the scores, online
-//     softmax in fp32 with exp2, write P as bf16 into a swizzled shared-memory tile (the A operand
-//     of the second MMA), rescale O in TMEM (tcgen05.ld / tcgen05.st);
+//     softmax in fp32 (packed fma/add.f32x2, MUFU exp2), P written back as 16-bit pairs into the first
+//     32 columns of the SAME S buffer (tcgen05.st) and consumed by the second MMA as a TMEM A operand
+//     -- no shared-memory P tile, no proxy fence, no wait on the previous P V; O is rescaled in TMEM
+//     lazily.  (Measured alternatives that lost: 8 softmax warps with two threads per row, -15 %;
+//     one-lane-per-warp mbarrier arrive/wait, no change.)
 //   * V is consumed as an MN-major B operand exactly as TMA delivers it (no transpose);
 //   * causal tiles above the diagonal are never loaded; causal / key-padding / tail masks are
 //     applied on the scores in registers; the (B,1,T,T) additive mask is never built.
 // Roofline: tensor pipe (2 * 2 * 128*128*hd flop per KV tile); the MUFU exp2 of the softmax is the
 // co-limiter (128*128 exps per tile at 16/clk/SM), see DESIGN.md.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace mmfs {
 
-#ifndef MMFS_ATTN_P_TMEM
-#define MMFS_ATTN_P_TMEM 1   // 1: P goes back into S's own TMEM columns and feeds the second MMA as a TMEM A operand
-#endif                       // 0: P staged in a swizzled shared-memory tile (the r01 kernel)
-constexpr bool kPTmem = MMFS_ATTN_P_TMEM != 0;
+constexpr bool kPTmem = true;       // P goes back into S's own TMEM columns and feeds the second MMA as a TMEM A operand
+                                    // (false: the first-generation path, P staged in a swizzled shared-memory tile)
 constexpr int kBM = 128, kBN = 64;  // 64-key tiles: 112 KB of shared memory and 256 TMEM columns per CTA -> 2 CTAs / SM
 constexpr int kAttnThreads = 192;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: softmax / epilogue
 constexpr uint32_t kTmemCols = 256; // S0 (64) | S1 (64) | O (<= 128)
@@ -45,6 +48,7 @@ struct AttnParams {
     int B, H, Tq, Tkv, causal, past;
     long o_bs, o_ts;
     float scale_log2e;         // scale * log2(e)
+    int debug;                 // timing experiments only (env MMFS_ATTN_DEBUG): 1 = no softmax math, 2 = no MMAs; results are garbage
 };
 
 template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
@@ -128,7 +132,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     uint8_t *s_kmask = reinterpret_cast<uint8_t *>(bars + 14);   // [2][64]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    // causal: the CTA scheduler hands out blockIdx.x in increasing order; launching the longest query tiles (most
+    // visible keys) first shortens the tail of the grid
+    const int m_tile = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int q0 = m_tile * kBM;
     // keys this query tile can see: causal -> j <= past + q; never beyond Tkv
     int kv_end = p.Tkv;
@@ -184,6 +190,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < HD / 16; ++kk) {
+                    if (p.debug & 2) break;
                     // 64-element box along hd, then 32 B inside the 128-byte swizzle atom
                     umma_f16(tmem_s0 + (uint32_t)s * kBN,
                              smem_desc(s_addr(sQ) + (kk >> 2) * QBOX_BYTES + (kk & 3) * 32, 16, 1024),
@@ -203,6 +210,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < kBN / 16; ++kk) {
+                    if (p.debug & 2) break;
                     // P: K-major, K = keys (one 64-key box).  V: MN-major, 16 key rows of 128 B per k-step,
                     // hd halves KBOX_BYTES apart (LBO)
                     const uint64_t v_desc = smem_desc(s_addr(sV) + s * KV_BYTES + kk * 16 * 128, KBOX_BYTES, 1024);
@@ -242,6 +250,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             }
             bar_wait(s_full + s, (j >> 1) & 1);
             tc_fence_after();
+            if (p.debug & 1) {      // keep lock-step with the MMA warp (p_full must not run two phases ahead)
+                if (j > 0) bar_wait(o_ready, (j - 1) & 1);
+                tc_fence_before(); bar_arrive(p_full); continue;
+            }
             // warp-uniform on purpose (lane 0 of the warp has the tightest causal limit): a per-lane condition makes
             // the compiler predicate the whole mask code into the hot loop (2.5x the instructions of an unmasked tile)
             const bool need_mask = (k0 + kBN - 1 > warp_causal_limit) || (k0 + kBN > p.Tkv) || (p.key_mask != nullptr);
@@ -418,6 +430,8 @@ extern "C" int mmfs_attn_forward(const void *q, const void *k, const void *v, vo
     AttnParams p;
     p.out = out; p.key_mask = key_mask; p.B = B; p.H = H; p.Tq = Tq; p.Tkv = Tkv; p.causal = causal; p.past = past;
     p.o_bs = o_bs; p.o_ts = o_ts; p.scale_log2e = scale * 1.4426950408889634f;
+    static const int debug = getenv("MMFS_ATTN_DEBUG") ? atoi(getenv("MMFS_ATTN_DEBUG")) : 0;
+    p.debug = debug;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MMFS_BF16) return hd == 64 ? launch_attn<__nv_bfloat16, 64>(mq, mk, mv, p, st) : launch_attn<__nv_bfloat16, 128>(mq, mk, mv, p, st);
     return hd == 64 ? launch_attn<__half, 64>(mq, mk, mv, p, st) : launch_attn<__half, 128>(mq, mk, mv, p, st);

@@ -235,13 +235,20 @@ __global__ void __launch_bounds__(256) rope_qk_kernel(T *__restrict__ q, T *__re
 template <typename T> __device__ __forceinline__ float silu_op(float g) { return __fdividef(g, 1.f + __expf(-g)); }
 template <> __device__ __forceinline__ float silu_op<float>(float g) { return g / (1.f + expf(-g)); }
 
-template <typename T>
+// GEGLU (diffusers FeedForward of the SD UNet): out = value * gelu(gate) with [value | gate] halves and the exact
+// erf GELU -- the same kernel with ACT = 1 and the gate in the second half.
+template <typename T, int ACT> __device__ __forceinline__ float glu_act(float g) {
+    if (ACT == 0) return silu_op<T>(g);
+    return 0.5f * g * (1.f + erff(g * 0.70710678118654752f));
+}
+
+template <typename T, int ACT = 0, bool GATE_SECOND = false>
 __global__ void __launch_bounds__(256) swiglu_kernel(const T *__restrict__ gu, T *__restrict__ out, long rows, int I) {
     // CTA per row (grid-stride): no 64-bit index division, two independent (gate, up) vector pairs in flight per thread
     constexpr int VEC = 16 / (int)sizeof(T);
     const int nvec = I / VEC;
     for (long r = blockIdx.x; r < rows; r += gridDim.x) {
-        const T *g_row = gu + r * 2 * I, *u_row = g_row + I;
+        const T *g_row = gu + r * 2 * I + (GATE_SECOND ? I : 0), *u_row = gu + r * 2 * I + (GATE_SECOND ? 0 : I);
         T *o_row = out + r * I;
         int i = threadIdx.x;
         for (; i + (int)blockDim.x < nvec; i += 2 * blockDim.x) {
@@ -251,18 +258,18 @@ __global__ void __launch_bounds__(256) swiglu_kernel(const T *__restrict__ gu, T
             float g[VEC], u[VEC], o[VEC];
             Vec16<T>::unpack(g0, g); Vec16<T>::unpack(u0, u);
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) o[k] = rnd<T>(silu_op<T>(g[k])) * u[k];   // act_fn(gate) is a tensor in T
+            for (int k = 0; k < VEC; ++k) o[k] = rnd<T>(glu_act<T, ACT>(g[k])) * u[k];   // act_fn(gate) is a tensor in T
             stg_v4(o_row + i * VEC, Vec16<T>::pack(o));
             Vec16<T>::unpack(g1, g); Vec16<T>::unpack(u1, u);
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) o[k] = rnd<T>(silu_op<T>(g[k])) * u[k];
+            for (int k = 0; k < VEC; ++k) o[k] = rnd<T>(glu_act<T, ACT>(g[k])) * u[k];
             stg_v4(o_row + j * VEC, Vec16<T>::pack(o));
         }
         if (i < nvec) {
             float g[VEC], u[VEC], o[VEC];
             Vec16<T>::unpack(ldg_nc_v4(g_row + i * VEC), g); Vec16<T>::unpack(ldg_nc_v4(u_row + i * VEC), u);
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) o[k] = rnd<T>(silu_op<T>(g[k])) * u[k];
+            for (int k = 0; k < VEC; ++k) o[k] = rnd<T>(glu_act<T, ACT>(g[k])) * u[k];
             stg_v4(o_row + i * VEC, Vec16<T>::pack(o));
         }
     }
@@ -297,11 +304,14 @@ static int launch_all(int which, const void *a, const void *b, const void *c, vo
                                                      (const int64_t *)c, n0, i0, i1, i2, i3, i4, i5);
             break;
         }
-        case 3: { // swiglu: a=gate_up d=out n0=rows i0=I
+        case 3: { // swiglu / geglu: a=gate_up d=out n0=rows i0=I i1=variant (0 silu [gate|up], 1 gelu [value|gate])
             const int nvec = i0 / (16 / (int)sizeof(T));
             const int threads = nvec >= 512 ? 256 : (nvec >= 64 ? 64 : 32);
             const int grid = (int)(n0 < 148L * 64 ? n0 : 148L * 64);
-            swiglu_kernel<T><<<grid, threads, 0, st>>>((const T *)a, (T *)d, n0, i0);
+            if (i1 == 1)
+                swiglu_kernel<T, 1, true><<<grid, threads, 0, st>>>((const T *)a, (T *)d, n0, i0);
+            else
+                swiglu_kernel<T, 0, false><<<grid, threads, 0, st>>>((const T *)a, (T *)d, n0, i0);
             break;
         }
     }
@@ -361,4 +371,13 @@ extern "C" int mmfs_swiglu(const void *gate_up, void *out, long rows, int inter,
     MMFS_CHECK_ARG(((uintptr_t)gate_up | (uintptr_t)out) % 16 == 0 && (inter * dtype_size(dtype)) % 16 == 0,
                    "swiglu: rows must be 16-byte aligned");
     return dispatch(dtype, 3, gate_up, nullptr, nullptr, out, nullptr, nullptr, rows, inter, 0, 0, 0, 0, 0, 0.f, stream);
+}
+
+extern "C" int mmfs_geglu(const void *value_gate, void *out, long rows, int inter, int dtype, void *stream) {
+    MMFS_CHECK_ARG(rows >= 0 && inter > 0, "geglu: bad shape");
+    if (rows == 0) return MMFS_OK;
+    MMFS_CHECK_ARG(value_gate && out, "geglu: null pointer argument");
+    MMFS_CHECK_ARG(((uintptr_t)value_gate | (uintptr_t)out) % 16 == 0 && (inter * dtype_size(dtype)) % 16 == 0,
+                   "geglu: rows must be 16-byte aligned");
+    return dispatch(dtype, 3, value_gate, nullptr, nullptr, out, nullptr, nullptr, rows, inter, 1, 0, 0, 0, 0, 0.f, stream);
 }

@@ -76,6 +76,19 @@ def swiglu(gate_up: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def geglu(value_gate: torch.Tensor) -> torch.Tensor:
+    """value * gelu(gate) (exact erf GELU) on a (..., 2*I) tensor holding [value | gate] (diffusers GEGLU)."""
+    _require(value_gate.is_cuda and value_gate.is_contiguous() and value_gate.shape[-1] % 2 == 0, "geglu: bad input")
+    inter = value_gate.shape[-1] // 2
+    out = torch.empty(value_gate.shape[:-1] + (inter,), dtype=value_gate.dtype, device=value_gate.device)
+    with torch.cuda.device(value_gate.device):
+        rc = _lib.lib().mmfs_geglu(value_gate.data_ptr(), out.data_ptr(), value_gate.numel() // (2 * inter), inter,
+                                   _DTYPE_CODE[value_gate.dtype], _stream())
+    _lib.check(rc, "geglu")
+    launch_counter[0] += 1
+    return out
+
+
 def attention(q, k, v, key_mask=None, causal=True, past=0, scale=None, force_generic=False) -> torch.Tensor:
     """softmax(q k^T * scale + mask) v.  q (B,Tq,H,hd), k/v (B,Tkv,H,hd) -- any batch / token strides, heads
     dense; key_mask (B,Tkv) bool/uint8 (1 = attend) or None; causal: query i sees keys j <= past + i.

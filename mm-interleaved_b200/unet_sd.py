@@ -123,7 +123,10 @@ class GEGLU(nn.Module):
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
     def forward(self, x):
-        h, gate = self.proj(x).chunk(2, dim=-1)
+        hg = self.proj(x)
+        if hg.is_cuda and hg.dtype != torch.float64 and (hg.shape[-1] // 2 * hg.element_size()) % 16 == 0:
+            return ops.geglu(hg.contiguous())
+        h, gate = hg.chunk(2, dim=-1)
         return h * F.gelu(gate)
 
 

@@ -96,3 +96,16 @@ def test_conv_kernel_path_matches_library_path_bf16():
     assert n_kernel - n_lib >= 14                                    # the res-block / sampler convs really took the kernel path
     err = (got.float() - want.float()).abs()
     assert err.max() <= 3e-2 * want.float().abs().max(), (err.max().item(), want.float().abs().max().item())
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 8e-3), (torch.float16, 1e-3)])
+def test_geglu_matches_torch(dtype, tol):
+    """value * gelu(gate) on [value | gate] vs the torch statements of diffusers' GEGLU; |err| <= tol * max(1, |ref|)."""
+    from mm_interleaved_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn((3, 37, 2 * 1280), generator=g) * 2).to(dtype)
+    out = ops.geglu(x.to(DEV))
+    h, gate = x.float().chunk(2, dim=-1)
+    ref = h * torch.nn.functional.gelu(gate)
+    err = (out.float().cpu() - ref).abs()
+    assert out.shape == (3, 37, 1280) and (err <= tol * ref.abs().clamp_min(1.0)).all(), err.max().item()

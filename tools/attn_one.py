@@ -13,6 +13,8 @@ SHAPES = {  # B, H, T, hd, causal
     "llama_cfg2": (1, 40, 512, 128, True),
     "clip": (16, 16, 257, 64, False),
     "sd_4096": (2, 5, 4096, 64, False),
+    "sd_b16": (16, 5, 4096, 64, False),
+    "llama_nc": (4, 40, 2048, 128, False),
 }
 name = sys.argv[1] if len(sys.argv) > 1 else "llama_cfg3"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
