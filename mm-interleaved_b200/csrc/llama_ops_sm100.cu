@@ -199,29 +199,37 @@ __global__ void __launch_bounds__(256) rope_qk_kernel(T *__restrict__ q, T *__re
     const int half = hd >> 1;
     const int chunks = half / VEC;
     const int per_tok = 2 * H * chunks;
+    // blockDim.x is a multiple of `chunks` whenever chunks is a power of two <= 32 (head sizes 64 / 128): a thread then
+    // keeps the same rotation chunk for every head it visits and loads the token's cos / sin values once per token
+    const bool hoist = (blockDim.x % chunks) == 0;
     for (long tok = blockIdx.x; tok < n_tok; tok += gridDim.x) {
         const long p = pos[pos_per_batch ? tok : (tok % T_len)];
         const float *cp = cos_t + p * hd, *sp = sin_t + p * hd;
         T *qt = q + tok * q_stride, *kt = k + tok * k_stride;
-        for (int it = threadIdx.x; it < per_tok; it += blockDim.x) {
-            const int c = it % chunks;
-            const int hh = it / chunks;                 // 0 .. 2H-1: q heads then k heads
-            T *x = (hh >= H ? kt + (size_t)(hh - H) * hd : qt + (size_t)hh * hd) + c * VEC;
-            float x1[VEC], x2[VEC], o1[VEC], o2[VEC], cs[VEC], sn[VEC];
-            Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(x), x1);
-            Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(x + half), x2);
+        float cs[VEC], sn[VEC];
+        auto load_table = [&](int c) {
 #pragma unroll
             for (int i = 0; i < VEC; i += 4) {
                 const float4 a = *reinterpret_cast<const float4 *>(cp + c * VEC + i);
                 const float4 b = *reinterpret_cast<const float4 *>(sp + c * VEC + i);
-                cs[i] = a.x; cs[i + 1] = a.y; cs[i + 2] = a.z; cs[i + 3] = a.w;
-                sn[i] = b.x; sn[i + 1] = b.y; sn[i + 2] = b.z; sn[i + 3] = b.w;
+                cs[i] = rnd<T>(a.x); cs[i + 1] = rnd<T>(a.y); cs[i + 2] = rnd<T>(a.z); cs[i + 3] = rnd<T>(a.w);   // tables cast to
+                sn[i] = rnd<T>(b.x); sn[i + 1] = rnd<T>(b.y); sn[i + 2] = rnd<T>(b.z); sn[i + 3] = rnd<T>(b.w);   // x.dtype (:141-144)
             }
+        };
+        if (hoist) load_table(threadIdx.x % chunks);
+        for (int it = threadIdx.x; it < per_tok; it += blockDim.x) {
+            const int c = it % chunks;
+            const int hh = it / chunks;                 // 0 .. 2H-1: q heads then k heads
+            T *x = (hh >= H ? kt + (size_t)(hh - H) * hd : qt + (size_t)hh * hd) + c * VEC;
+            float x1[VEC], x2[VEC], o1[VEC], o2[VEC];
+            const uint4 v1 = *reinterpret_cast<const uint4 *>(x), v2 = *reinterpret_cast<const uint4 *>(x + half);
+            if (!hoist) load_table(c);
+            Vec16<T>::unpack(v1, x1);
+            Vec16<T>::unpack(v2, x2);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                const float c_ = rnd<T>(cs[i]), s_ = rnd<T>(sn[i]);      // tables cast to x.dtype (:141-144)
-                o1[i] = rnd<T>(x1[i] * c_) + rnd<T>(-x2[i] * s_);
-                o2[i] = rnd<T>(x2[i] * c_) + rnd<T>(x1[i] * s_);
+                o1[i] = rnd<T>(x1[i] * cs[i]) + rnd<T>(-x2[i] * sn[i]);
+                o2[i] = rnd<T>(x2[i] * cs[i]) + rnd<T>(x1[i] * sn[i]);
             }
             *reinterpret_cast<uint4 *>(x) = Vec16<T>::pack(o1);
             *reinterpret_cast<uint4 *>(x + half) = Vec16<T>::pack(o2);
@@ -229,7 +237,6 @@ __global__ void __launch_bounds__(256) rope_qk_kernel(T *__restrict__ q, T *__re
     }
 }
 
-// ---- SwiGLU: out = silu(gate) * up, gate|up stored as one (rows, 2*I) GEMM output -------------------
 // silu in fp32: exact expf / division for fp32 tensors; ex2.approx + rcp.approx for 16-bit tensors, whose result is
 // rounded to 8 / 11 significand bits right after (relative error of the fast path ~2^-21).
 template <typename T> __device__ __forceinline__ float silu_op(float g) { return __fdividef(g, 1.f + __expf(-g)); }

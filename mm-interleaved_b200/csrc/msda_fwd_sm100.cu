@@ -147,6 +147,69 @@ msda_fwd_rows_kernel(const T *__restrict__ value, const int64_t *__restrict__ sh
 }
 
 // ------------------------------------------------------------------------------------
+// Small rows (L*P <= kSmallLP: the ViT-Adapter's injector / extractor, 12 and 4 points per row): one THREAD per
+// (output row, 16-byte channel vector).  A warp-per-row pass would leave 20-28 of its 32 point lanes idle and pay the
+// staging / mailbox / barrier sequence for 4 points; here a row costs its own loads only, the index math is repeated
+// by the D*sizeof(T)/16 threads of a row (cheap at <= 16 points) and latency is hidden by occupancy, not by staging.
+// Same index math (point_geom, corner_valid) and fp32 opmath as the row kernel; zero-weight points skipped alike.
+// ------------------------------------------------------------------------------------
+constexpr int kSmallLP = 16;
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256)
+msda_fwd_smallrow_kernel(const T *__restrict__ value, const int64_t *__restrict__ shapes,
+                         const int64_t *__restrict__ starts, const T *__restrict__ loc,
+                         const T *__restrict__ attn, T *__restrict__ out,
+                         long total, int S, int M, int L, int Lq, int P, unsigned flags) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int LPR = D / VEC;
+    const bool strict = flags & MMFS_MSDA_STRICT;
+    const int LP = L * P;
+    const long long row_elems = (long long)M * D;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long row = idx / LPR;                 // (b * Lq + q) * M + m
+        const int v = (int)(idx % LPR);
+        const int m = (int)(row % M);
+        const long b = row / ((long)M * Lq);
+        const T *loc_row = loc + row * LP * 2;
+        const T *att_row = attn + row * LP;
+        const T *slab = value + ((size_t)b * S * M + m) * D + v * VEC;
+        float acc[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+        int j = 0;
+        for (int l = 0; l < L; ++l) {
+            const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1], start = (int)starts[l];
+            for (int pp = 0; pp < P; ++pp, ++j) {
+                const float a = elem_to_f32(att_row + j);
+                if (!strict && a == 0.f) continue;
+                const PointGeom<float> g = point_geom(elem_to_f32(loc_row + 2 * j), elem_to_f32(loc_row + 2 * j + 1), H, W);
+                if (!g.in_range) continue;
+                const float hh = 1.f - g.lh, hw = 1.f - g.lw;
+                const T *p00 = slab + (long long)(start + g.h_low * W + g.w_low) * row_elems;
+                uint4 vv[4];
+                float wk[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool ok = corner_valid(k, g.h_low, g.w_low, H, W);
+                    wk[k] = ok ? ((k & 2) ? g.lh : hh) * ((k & 1) ? g.lw : hw) * a : 0.f;
+                    const T *pk = p00 + ((k & 2) ? (long long)W * row_elems : 0ll) + ((k & 1) ? row_elems : 0ll);
+                    vv[k] = ok ? ldg_nc_v4(pk) : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float f[VEC];
+                    Vec16<T>::unpack(vv[k], f);
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) acc[c] = fmaf(wk[k], f[c], acc[c]);
+                }
+            }
+        }
+        stg_v4(out + row * D + v * VEC, Vec16<T>::pack(acc));
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // Generic path (any D, f64): one thread per output scalar, index math per thread.
 // ------------------------------------------------------------------------------------
 template <typename T>
@@ -292,6 +355,20 @@ static int dispatch_d(const void *value, const int64_t *shapes, const int64_t *s
 #define MMFS_CASE(DD) \
     case DD: return launch_rows<T, DD>(value, shapes, starts, loc, attn, out, N, S, M, L, Lq, P, flags, st);
     const bool aligned16 = ((uintptr_t)value % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    if (aligned16 && L * P <= kSmallLP && g_rows_per_warp == 0 && (D == 32 || D == 64 || D == 128)) {
+        constexpr int VEC = 16 / (int)sizeof(T);
+        const long total = (long)N * Lq * M * (D / VEC);
+        const long blocks = (total + 255) / 256;
+        const int grid = (int)(blocks < (long)num_sms() * 64 ? blocks : (long)num_sms() * 64);
+        if (D == 32)
+            msda_fwd_smallrow_kernel<T, 32><<<grid, 256, 0, st>>>((const T *)value, shapes, starts, (const T *)loc, (const T *)attn, (T *)out, total, S, M, L, Lq, P, flags);
+        else if (D == 64)
+            msda_fwd_smallrow_kernel<T, 64><<<grid, 256, 0, st>>>((const T *)value, shapes, starts, (const T *)loc, (const T *)attn, (T *)out, total, S, M, L, Lq, P, flags);
+        else
+            msda_fwd_smallrow_kernel<T, 128><<<grid, 256, 0, st>>>((const T *)value, shapes, starts, (const T *)loc, (const T *)attn, (T *)out, total, S, M, L, Lq, P, flags);
+        MMFS_CUDA(cudaGetLastError());
+        return MMFS_OK;
+    }
     if (aligned16) {
         switch (D) {
             MMFS_CASE(32)
