@@ -36,6 +36,9 @@ CASES = [
     (1, 5, 512, 512, 128, True, 0, False),      # cfg 2 prefill length
     (1, 2, 1024, 77, 64, False, 0, False),      # SD cross-attention: kv = 77
     (1, 2, 2048, 2048, 128, True, 0, False),    # cfg 3 prefill length
+    (2, 2, 640, 640, 128, True, 0, True),       # five query tiles, padding mask
+    (1, 3, 1000, 1000, 64, False, 0, False),    # ragged tails of the last query tile and of the key tiles
+    (1, 2, 384, 900, 128, True, 516, True),     # chunked prefill on a cache
 ]
 
 

@@ -191,6 +191,23 @@ def test_tuning_variants_bit_identical():
         lib.mmfs_msda_set_tuning(0, 0)
 
 
+@pytest.mark.parametrize("case", [0, 3, 5, 7])
+def test_small_row_kernel_agrees_with_row_kernel(case):
+    """L*P <= 16 rows take the thread-per-output-vector kernel; a non-zero rows_per_warp forces the warp-per-row
+    kernel on the same inputs.  Same index math, different fp32 summation order: |diff| <= 2e-6 + 2e-5 |ref| (fp32)."""
+    m = _mod()
+    lib = m._lib.lib()
+    N, shapes, M, D, Lq, P = CASES[case]
+    v, s, st, loc, a = make_msda_inputs(N, shapes, M, D, Lq, P, seed=20 + case, loc_mode="edges")
+    small = run_cuda(v, s, st, loc, a, torch.float32)
+    try:
+        assert lib.mmfs_msda_set_tuning(2, 0) == 0
+        rows = run_cuda(v, s, st, loc, a, torch.float32)
+    finally:
+        lib.mmfs_msda_set_tuning(0, 0)
+    assert ((small - rows).abs() <= 2e-6 + 2e-5 * rows.abs()).all()
+
+
 def test_full_size_properties_cfg3():
     """BASELINE cfg 3 layer shape (L=12, S=5376, Lq=2048, M=16, D=64, P=8), 2 sequences: size-
     independent properties instead of an element-wise oracle run."""
