@@ -118,8 +118,12 @@ __global__ void __launch_bounds__(kRmsThreads) rmsnorm_reg_kernel(const T *__res
 // path -- every LayerNorm on the interleaved path (64 ... 1280 columns); longer or unaligned rows use the block kernel.
 constexpr int kLnChunks = 8;
 
-template <typename T>
-__global__ void __launch_bounds__(256) layernorm_warp_kernel(const T *__restrict__ x, const T *__restrict__ w,
+// CH = 16-byte vectors per lane (1, 2, 4 or 8: rows of up to 32*CH*VEC elements).  The row is kept as raw 16-byte
+// registers and unpacked three times (sum, centred squares, output): 4 registers per vector instead of 8 floats, so
+// the common CH <= 4 instantiations stay under 64 registers and 32+ warps per SM hide the load latency (the first
+// version held the row as floats for CH = 8 always: 126 registers, 16 warps per SM, 1.1-1.5 TB/s).
+template <typename T, int CH>
+__global__ void __launch_bounds__(256, CH == 8 ? 2 : 4) layernorm_warp_kernel(const T *__restrict__ x, const T *__restrict__ w,
                                                               const T *__restrict__ b, T *__restrict__ y, long rows, int cols, float eps) {
     constexpr int VEC = 16 / (int)sizeof(T);
     const int lane = threadIdx.x & 31;
@@ -127,41 +131,47 @@ __global__ void __launch_bounds__(256) layernorm_warp_kernel(const T *__restrict
     if (row >= rows) return;
     const T *xr = x + row * cols;
     T *yr = y + row * cols;
-    const int nvec = cols / VEC;                 // host guarantees cols % VEC == 0 and nvec <= 32 * kLnChunks
-    float v[kLnChunks][VEC];
+    const int nvec = cols / VEC;                 // host guarantees cols % VEC == 0 and nvec <= 32 * CH
+    uint4 v[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const int i = lane + 32 * c;
+        v[c] = (i < nvec) ? ldg_nc_v4(xr + i * VEC) : make_uint4(0u, 0u, 0u, 0u);
+    }
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < kLnChunks; ++c) {
-        const int i = lane + 32 * c;
-        if (i < nvec) {
-            Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(xr + i * VEC), v[c]);
+    for (int c = 0; c < CH; ++c) {               // padding vectors are zeros: they add nothing to the sum
+        float f[VEC];
+        Vec16<T>::unpack(v[c], f);
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) s += v[c][k];
-        }
+        for (int k = 0; k < VEC; ++k) s += f[k];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s / (float)cols;
     float ss = 0.f;
 #pragma unroll
-    for (int c = 0; c < kLnChunks; ++c)
+    for (int c = 0; c < CH; ++c)
         if (lane + 32 * c < nvec) {
+            float f[VEC];
+            Vec16<T>::unpack(v[c], f);
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) { const float d = v[c][k] - mean; ss += d * d; }
+            for (int k = 0; k < VEC; ++k) { const float d = f[k] - mean; ss = fmaf(d, d, ss); }
         }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float r = rsqrtf(ss / (float)cols + eps);
 #pragma unroll
-    for (int c = 0; c < kLnChunks; ++c) {
+    for (int c = 0; c < CH; ++c) {
         const int i = lane + 32 * c;
         if (i < nvec) {
-            float g[VEC], bb[VEC], o[VEC];
+            float f[VEC], g[VEC], bb[VEC], o[VEC];
+            Vec16<T>::unpack(v[c], f);
             if (w) Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(w + i * VEC), g);
             if (b) Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(b + i * VEC), bb);
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) o[k] = (v[c][k] - mean) * r * (w ? g[k] : 1.f) + (b ? bb[k] : 0.f);
-            *reinterpret_cast<uint4 *>(yr + i * VEC) = Vec16<T>::pack(o);
+            for (int k = 0; k < VEC; ++k) o[k] = (f[k] - mean) * r * (w ? g[k] : 1.f) + (b ? bb[k] : 0.f);
+            stg_v4(yr + i * VEC, Vec16<T>::pack(o));
         }
     }
 }
@@ -297,9 +307,13 @@ static int launch_all(int which, const void *a, const void *b, const void *c, vo
             constexpr int VEC = 16 / (int)sizeof(T);
             const bool vec_ok = (i0 % VEC == 0) && (i0 / VEC <= 32 * kLnChunks) &&
                                 (((uintptr_t)a | (uintptr_t)d | (uintptr_t)b | (uintptr_t)c) % 16 == 0);
-            if (vec_ok)
-                layernorm_warp_kernel<T><<<(unsigned)((n0 + 7) / 8), 256, 0, st>>>((const T *)a, (const T *)b, (const T *)c, (T *)d, n0, i0, eps);
-            else
+            if (vec_ok) {
+                const int nvec = i0 / VEC;
+                const unsigned grid = (unsigned)((n0 + 7) / 8);
+#define MMFS_LN(CH) layernorm_warp_kernel<T, CH><<<grid, 256, 0, st>>>((const T *)a, (const T *)b, (const T *)c, (T *)d, n0, i0, eps)
+                if (nvec <= 32) MMFS_LN(1); else if (nvec <= 64) MMFS_LN(2); else if (nvec <= 128) MMFS_LN(4); else MMFS_LN(8);
+#undef MMFS_LN
+            } else
                 layernorm_kernel<T><<<(unsigned)n0, 256, 0, st>>>((const T *)a, (const T *)b, (const T *)c, (T *)d, i0, eps);
             break;
         }
