@@ -10,8 +10,8 @@
 // Thread mapping (both kernels): thread t owns the 16-byte channel vector t % (C/VEC) of every k-th pixel, so the
 // per-channel scale/shift (apply) and the partial sums (statistics) live in registers and consecutive threads
 // read consecutive 16-byte vectors of a pixel row (coalesced).  Statistics are fp32 sum / sum-of-squares, reduced
-// per group through shared then global atomics; the bf16 pipeline's rounding points (norm -> T, silu -> T) are
-// kept so a bf16 run tracks diffusers' bf16 run.
+// in a fixed order (no atomics: results are reproducible run to run); the bf16 pipeline's rounding points
+// (norm -> T, silu -> T) are kept so a bf16 run tracks diffusers' bf16 run.
 #include "common.cuh"
 
 namespace mmfs {
@@ -19,14 +19,18 @@ namespace mmfs {
 template <typename T> __device__ __forceinline__ float gn_rnd(float x) { return to_op(from_op<T>(x)); }
 template <> __device__ __forceinline__ float gn_rnd<float>(float x) { return x; }
 
+constexpr int kGnMaxChunks = 64;     // pixel chunks per image: the partial-statistics scratch is (B, kGnMaxChunks, G, 2) floats
+
+// Pass 1: per (image, pixel chunk) partial sum / sum of squares of every group, written (not accumulated) to
+// partial[b][chunk][g][0..1].  All reductions run in a fixed order -- registers over a thread's pixels, shared memory
+// over the pixel lanes of a channel, then over the channels of a group -- so the result is bit-reproducible run to run
+// (the first version used shared + global float atomics, whose order is not).
 template <typename T>
-__global__ void __launch_bounds__(1024) gn_stats_kernel(const T *__restrict__ x, float *__restrict__ stats, int HW, int C,
+__global__ void __launch_bounds__(1024) gn_stats_kernel(const T *__restrict__ x, float *__restrict__ partial, int HW, int C,
                                                          int G, int ppb, int cvecs, int lanes) {
     constexpr int VEC = 16 / (int)sizeof(T);
-    extern __shared__ float s_acc[];                     // [G][2]
+    extern __shared__ float s_dyn[];                     // [lanes][C][2] thread partials, then [C][2] channel sums in place of lane 0
     const int b = blockIdx.y, p0 = blockIdx.x * ppb, p1 = min(HW, p0 + ppb);
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_acc[i] = 0.f;
-    __syncthreads();
     const int cv = threadIdx.x % cvecs, pl = threadIdx.x / cvecs;
     float s[VEC], ss[VEC];
 #pragma unroll
@@ -52,29 +56,46 @@ __global__ void __launch_bounds__(1024) gn_stats_kernel(const T *__restrict__ x,
 #pragma unroll
             for (int k = 0; k < VEC; ++k) { s[k] += f[k]; ss[k] = fmaf(f[k], f[k], ss[k]); }
         }
-        const int cg = C / G;
-        int g = (cv * VEC) / cg;
-        float a = 0.f, q = 0.f;
+        float *mine = s_dyn + ((size_t)pl * C + (size_t)cv * VEC) * 2;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {                  // flush run-wise: a vector spans at most a few groups
-            const int gk = (cv * VEC + k) / cg;
-            if (gk != g) { atomicAdd(&s_acc[2 * g], a); atomicAdd(&s_acc[2 * g + 1], q); a = q = 0.f; g = gk; }
-            a += s[k]; q += ss[k];
-        }
-        atomicAdd(&s_acc[2 * g], a); atomicAdd(&s_acc[2 * g + 1], q);
+        for (int k = 0; k < VEC; ++k) { mine[2 * k] = s[k]; mine[2 * k + 1] = ss[k]; }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&stats[(size_t)b * 2 * G + i], s_acc[i]);
+    if (pl == 0) {                                       // channel totals over the pixel lanes, lane order
+        for (int l = 1; l < lanes; ++l) {
+            const float *o = s_dyn + ((size_t)l * C + (size_t)cv * VEC) * 2;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) { s[k] += o[2 * k]; ss[k] += o[2 * k + 1]; }
+        }
+        float *mine = s_dyn + (size_t)cv * VEC * 2;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { mine[2 * k] = s[k]; mine[2 * k + 1] = ss[k]; }
+    }
+    __syncthreads();
+    const int cg = C / G;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) {   // group totals over the group's channels, channel order
+        const int g = i >> 1, which = i & 1;
+        float acc = 0.f;
+        for (int c = 0; c < cg; ++c) acc += s_dyn[(size_t)(g * cg + c) * 2 + which];
+        partial[(((size_t)b * kGnMaxChunks + blockIdx.x) * G + g) * 2 + which] = acc;
+    }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(1024) gn_apply_kernel(const T *__restrict__ x, const T *__restrict__ gamma,
-                                                         const T *__restrict__ beta, const float *__restrict__ stats,
+                                                         const T *__restrict__ beta, const float *__restrict__ partial,
                                                          T *__restrict__ y, int HW, int C, int G, int ppb, int cvecs, int lanes,
-                                                         float eps, int silu) {
+                                                         float eps, int silu, int chunks) {
     constexpr int VEC = 16 / (int)sizeof(T);
+    extern __shared__ float stats[];                     // [G][2] totals of this image (chunk order: reproducible)
     const int b = blockIdx.y, p0 = blockIdx.x * ppb, p1 = min(HW, p0 + ppb);
     const int cv = threadIdx.x % cvecs, pl = threadIdx.x / cvecs;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) {
+        float acc = 0.f;
+        for (int ch = 0; ch < chunks; ++ch) acc += partial[((size_t)b * kGnMaxChunks + ch) * 2 * G + i];
+        stats[i] = acc;
+    }
+    __syncthreads();
     if (pl >= lanes) return;
     const int cg = C / G;
     const float inv_n = 1.f / ((float)cg * (float)HW);
@@ -88,8 +109,8 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const T *__restrict__ x,
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
             const int g = (cv * VEC + k) / cg;
-            const float mean = stats[((size_t)b * G + g) * 2] * inv_n;
-            const float var = fmaxf(stats[((size_t)b * G + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+            const float mean = stats[2 * g] * inv_n;
+            const float var = fmaxf(stats[2 * g + 1] * inv_n - mean * mean, 0.f);
             const float r = rsqrtf(var + eps);
             sc[k] = r * gm[k];
             sh[k] = bt[k] - mean * sc[k];
@@ -129,13 +150,16 @@ static int gn_launch(const void *x, const void *gamma, const void *beta, void *y
     const int threads = cvecs * lanes;
     const int target_blocks = max(1, (num_sms() * 8) / B);               // ~8 CTAs' worth of work per SM over the batch
     int ppb = max(lanes * 4, (HW + target_blocks - 1) / target_blocks);
+    ppb = max(ppb, (HW + kGnMaxChunks - 1) / kGnMaxChunks);
     ppb = min(ppb, HW);
-    const int chunks = (HW + ppb - 1) / ppb;
-    MMFS_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)B * G, st));
+    const int chunks = (HW + ppb - 1) / ppb;             // <= kGnMaxChunks
+    const size_t smem_stats = (size_t)lanes * C * 2 * sizeof(float);
+    auto kern = gn_stats_kernel<T>;
+    if (smem_stats > 48 * 1024) MMFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stats));
     dim3 grid(chunks, B);
-    gn_stats_kernel<T><<<grid, threads, 2 * G * sizeof(float), st>>>((const T *)x, stats, HW, C, G, ppb, cvecs, lanes);
-    gn_apply_kernel<T><<<grid, threads, 0, st>>>((const T *)x, (const T *)gamma, (const T *)beta, stats, (T *)y, HW, C, G, ppb,
-                                                 cvecs, lanes, eps, silu);
+    kern<<<grid, threads, smem_stats, st>>>((const T *)x, stats, HW, C, G, ppb, cvecs, lanes);
+    gn_apply_kernel<T><<<grid, threads, 2 * G * sizeof(float), st>>>((const T *)x, (const T *)gamma, (const T *)beta, stats, (T *)y,
+                                                                    HW, C, G, ppb, cvecs, lanes, eps, silu, chunks);
     MMFS_CUDA(cudaGetLastError());
     return MMFS_OK;
 }

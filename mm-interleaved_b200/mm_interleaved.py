@@ -71,6 +71,67 @@ def pack_mmfs_features(multiscale_features: Sequence[torch.Tensor], spatial_shap
     return torch.cat(packed, dim=2)
 
 
+def sincos_pos_embed_1d(embed_dim: int, length: int) -> torch.Tensor:
+    """(length, embed_dim) [sin | cos] table of ``get_1d_sincos_pos_embed_from_grid`` (utils/pos_embed.py:77-95) for
+    positions 0..length-1 (float32 arithmetic like the numpy original)."""
+    import numpy as np
+    omega = np.arange(embed_dim // 2, dtype=np.float32)
+    omega /= embed_dim / 2.0
+    omega = 1.0 / 10000 ** omega
+    out = np.einsum("m,d->md", np.arange(length, dtype=np.float32), omega)
+    return torch.from_numpy(np.concatenate([np.sin(out), np.cos(out)], axis=1))
+
+
+def soi_positions(text_ids: torch.Tensor, soi_token_id: int, n_images: int):
+    """Row / column of the first ``n_images`` ``<soi>`` tokens in row-major order, without ``nonzero`` (no host sync:
+    the image count is known from the image tensor)."""
+    B, L = text_ids.shape
+    flat = torch.where((text_ids == soi_token_id).reshape(-1), torch.arange(B * L, device=text_ids.device), B * L)
+    flat = flat.sort().values[:n_images]
+    return flat // L, flat % L
+
+
+def context_features_for_image_decoder(context_features: torch.Tensor, text_ids: torch.Tensor, soi_token_id: int,
+                                       context_feat_proj: nn.Module, seq_len: int, n_images: int,
+                                       nearest_bos_idxs: Optional[torch.Tensor] = None, pad_to: Optional[int] = None):
+    """``_prepare_context_features_for_image_decoder`` (mm_interleaved.py:254-304): for every image, the decoder hidden
+    states from its nearest ``<bos>`` (default: position 0) up to and including its ``<soi>``, in REVERSED order (the
+    ``<soi>`` state first), zero-padded to the longest context, through ``context_feat_proj`` (padding rows included,
+    as in the reference) plus the 1-D sin-cos table.  Returns (features (B_I, L_max, C), mask (B_I, L_max) int64).
+    ``pad_to`` fixes L_max (no host sync); None reproduces the reference's data-dependent ``max(context_lengths)``."""
+    rows, cols = soi_positions(text_ids, soi_token_id, n_images)
+    bos = torch.zeros_like(cols) if nearest_bos_idxs is None else nearest_bos_idxs.to(cols.dtype)
+    lengths = cols - bos + 1
+    L_max = int(lengths.max()) if pad_to is None else int(pad_to)
+    t = torch.arange(L_max, device=text_ids.device)
+    src = cols[:, None] - t[None, :]                                   # reversed walk from the <soi> position
+    valid = t[None, :] < lengths[:, None]
+    gathered = context_features[rows[:, None], src.clamp(min=0)]       # (B_I, L_max, C)
+    per_image = torch.where(valid[..., None], gathered, torch.zeros((), dtype=gathered.dtype, device=gathered.device))
+    pos = sincos_pos_embed_1d(context_features.shape[-1], seq_len).to(device=per_image.device, dtype=per_image.dtype)
+    per_image = context_feat_proj(per_image) + pos[None, :L_max]
+    return per_image, valid.to(cols.dtype)
+
+
+def mmfs_features_for_image_decoder(multiscale_features: Sequence[torch.Tensor], text_ids: torch.Tensor, soi_token_id: int,
+                                    nearest_bos_idxs: Optional[torch.Tensor] = None):
+    """``_prepare_mmfs_features_for_image_decoder`` (mm_interleaved.py:306-340): the tril/triu pair keeps exactly one
+    candidate per image -- the image right before it in row-major order -- and it is used iff its ``<soi>`` lies at or
+    after the current image's context start (``row * L + nearest_bos``).  Returns ([ (B_I, 1, C, h, w) ], (B_I, 1))."""
+    n = multiscale_features[0].shape[0]
+    L = text_ids.shape[1]
+    rows, cols = soi_positions(text_ids, soi_token_id, n)
+    start = rows * L + (torch.zeros_like(cols) if nearest_bos_idxs is None else nearest_bos_idxs.to(cols.dtype))
+    flat = rows * L + cols
+    prev = torch.arange(n, device=text_ids.device) - 1
+    use = (prev >= 0) & (start <= flat[prev.clamp(min=0)])             # image_context_mask[i, i-1]
+    feats = []
+    for f in multiscale_features:
+        g = f[prev.clamp(min=0)] * use.view(-1, 1, 1, 1).to(f.dtype)
+        feats.append(g[:, None])
+    return feats, use.to(torch.long)[:, None]
+
+
 class TextHead(nn.Module):
     """``TextDecoder`` (decoders/decoder_text.py): ``head`` over the original vocabulary plus ``head_new`` for the
     added ids, summed on the tail columns (:155-157).  State-dict names match the reference."""
@@ -103,12 +164,51 @@ class TextHead(nn.Module):
         return F.linear(hidden_states, self._fused_weight())[..., :self.head.weight.shape[0]]
 
 
+class ImageDecoder(nn.Module):
+    """``ImageDecoder`` (decoders/decoder_image.py:9-156) on this repo's modules: ``perceiver_resampler`` (Q-Former, 77
+    queries of width 1024 over the per-image LLM context), ``neg_prompt_embeds`` and ``decoder`` = the SD UNet with
+    its MMFS network (decoders/sd.py:20-140).  The VAE and the noise scheduler are diffusers objects that are not part
+    of this repository: ``generate_images`` returns the denoised LATENTS (``output_type="latent"`` of the patched
+    pipeline, sd.py:196-211) and applies ``vae_decode`` if the caller supplies one."""
+
+    def __init__(self, perceiver_config=None, seq_len=77, embed_dim=1024, unet=None, mmfs_module=None, image_size=512,
+                 base_seed=0):
+        super().__init__()
+        from .visual_tokenizer import PerceiverResampler
+        self.perceiver_resampler = PerceiverResampler(**(perceiver_config or dict(num_queries=seq_len, hidden_size=embed_dim)))
+        self.neg_prompt_embeds = nn.Parameter(torch.zeros(1, seq_len, embed_dim).normal_(0, 0.02))
+        self.unet, self.mmfs_module = unet, mmfs_module
+        self.image_size, self.base_seed = image_size, base_seed
+
+    @torch.no_grad()
+    def generate_images(self, context_features, context_attention_mask=None, mmfs_features=None, mmfs_mask=None,
+                        num_inference_steps=30, guidance_scale=7.5, latents=None, vae_decode=None, **_):
+        from .unet_sd import denoise_loop
+        text_embeds = self.perceiver_resampler(encoder_hidden_states=context_features,
+                                               encoder_attention_mask=context_attention_mask)[0]        # decoder_image.py:132-136
+        neg = self.neg_prompt_embeds.to(text_embeds.dtype).expand_as(text_embeds)                       # :141-143
+        n = text_embeds.shape[0]
+        if latents is None:
+            g = torch.Generator(device=text_embeds.device).manual_seed(self.base_seed)                  # sd.py:166-169
+            side = self.image_size // 8
+            latents = torch.randn((n, 4, side, side), generator=g, device=text_embeds.device, dtype=text_embeds.dtype)
+        if latents.is_cuda:
+            latents = latents.contiguous(memory_format=torch.channels_last)
+        lat = denoise_loop(self.unet, latents, text_embeds, neg, mmfs_features, mmfs_mask, self.mmfs_module,
+                           num_steps=num_inference_steps, guidance=guidance_scale)
+        out = {"latents": lat}
+        if vae_decode is not None:                                                                      # sd.py:212-216
+            out["image"] = (vae_decode(lat.float() / 0.18215) / 2 + 0.5).clamp(0, 1)
+        return out
+
+
 class InterleavedForward(nn.Module):
     """``mm_decoder`` + ``text_decoder`` + ``soi_token`` of ``MMInterleaved`` with the forward path of
     ``MMInterleaved.forward`` up to the text logits.  Image embeddings / multi-scale maps come from the visual
     tokenizer (``visual_output`` dict with ``vis_embed`` and ``multiscale_features``, visual_tokenizer.py:96-101)."""
 
-    def __init__(self, config: LlamaMMFSConfig, special_tokens=None, orig_vocab_size: int = 32000):
+    def __init__(self, config: LlamaMMFSConfig, special_tokens=None, orig_vocab_size: int = 32000, seq_len: int = 2048,
+                 image_decoder: Optional[nn.Module] = None):
         super().__init__()
         self.config = config
         self.special_token_dict = dict(DEFAULT_SPECIAL_TOKENS if special_tokens is None else special_tokens)
@@ -116,6 +216,9 @@ class InterleavedForward(nn.Module):
         self.text_decoder = TextHead(config.hidden_size, config.vocab_size, orig_vocab_size)
         self.soi_token = nn.Parameter(torch.zeros(1, config.hidden_size))
         self.spatial_shapes = list(config.spatial_shapes)
+        self.context_feat_proj = nn.Linear(config.hidden_size, config.hidden_size)       # mm_interleaved.py:99
+        self.seq_len = seq_len
+        self.image_decoder = image_decoder                                                # ImageDecoder or None
 
     def prepare(self, text_ids, visual_output, num_image_per_seq, max_num_image: int):
         st = self.special_token_dict
@@ -133,6 +236,31 @@ class InterleavedForward(nn.Module):
         out = self.mm_decoder(inputs_embeds=mm_embeds, attention_mask=attention_mask, vision_hidden_states=feats,
                               cross_attention_mask=cross, use_cache=False, return_dict=True)
         return self.text_decoder(out.last_hidden_state)
+
+    @torch.no_grad()
+    def generate_images(self, text_ids, visual_output, num_image_per_seq, max_num_image: int, attention_mask=None,
+                        target_image_idxs=None, **kwargs):
+        """``MMInterleaved.generate_images`` (mm_interleaved.py:520-596): decoder prefill over the interleaved context,
+        per-image reversed context features (:254-304) and previous-image MMFS features (:306-340), optional selection
+        of target images, then ``ImageDecoder.generate_images`` (Q-Former -> CFG denoise loop with the MMFS network)."""
+        if self.image_decoder is None:
+            raise RuntimeError("generate_images needs an image_decoder (ImageDecoder with a UNet and an MMFSNet)")
+        st = self.special_token_dict
+        mm_embeds, cross, feats = self.prepare(text_ids, visual_output, num_image_per_seq, max_num_image)
+        hidden = self.mm_decoder(inputs_embeds=mm_embeds, attention_mask=attention_mask, vision_hidden_states=feats,
+                                 cross_attention_mask=cross, use_cache=False, return_dict=True).last_hidden_state
+        ms = visual_output["multiscale_features"]
+        n_img = ms[0].shape[0]
+        mmfs_features, mmfs_mask = mmfs_features_for_image_decoder(ms, text_ids, st["soi_token_id"])
+        ctx, ctx_mask = context_features_for_image_decoder(hidden, text_ids, st["soi_token_id"], self.context_feat_proj,
+                                                           self.seq_len, n_img, pad_to=kwargs.pop("context_pad_to", None))
+        if target_image_idxs is not None:
+            ctx, ctx_mask, mmfs_mask = (torch.index_select(t, 0, target_image_idxs) for t in (ctx, ctx_mask, mmfs_mask))
+            mmfs_features = [torch.index_select(f, 0, target_image_idxs) for f in mmfs_features]
+        out = self.image_decoder.generate_images(context_features=ctx, context_attention_mask=ctx_mask,
+                                                 mmfs_features=mmfs_features, mmfs_mask=mmfs_mask, **kwargs)
+        out.update(context_features=ctx, context_attention_mask=ctx_mask, mmfs_mask=mmfs_mask)
+        return out
 
     @torch.no_grad()
     def generate_texts(self, text_ids, visual_output, num_image_per_seq, max_num_image: int, attention_mask=None,

@@ -168,7 +168,7 @@ def group_norm_nhwc(x: torch.Tensor, groups: int, weight=None, bias=None, eps: f
     _require(group_norm_supported(x), "group_norm_nhwc: need a CUDA channels_last f32/f16/bf16 tensor with C % (16/size) == 0")
     B, C, H, W = x.shape
     y = torch.empty_like(x, memory_format=torch.channels_last)
-    stats = torch.empty((B, groups, 2), dtype=torch.float32, device=x.device)
+    stats = torch.empty((B, 64, groups, 2), dtype=torch.float32, device=x.device)   # per-chunk partial sums
     with torch.cuda.device(x.device):
         rc = _lib.lib().mmfs_groupnorm_nhwc(x.data_ptr(), weight.data_ptr() if weight is not None else None,
                                             bias.data_ptr() if bias is not None else None, y.data_ptr(), stats.data_ptr(),

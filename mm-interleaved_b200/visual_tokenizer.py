@@ -411,7 +411,8 @@ class QFormerAttention(nn.Module):
         self.q_norm = nn.LayerNorm(self.attention_head_size, eps=eps) if qk_norm else nn.Identity()
         self.k_norm = nn.LayerNorm(self.attention_head_size, eps=eps) if qk_norm else nn.Identity()
 
-    def forward(self, hidden_states, encoder_hidden_states=None):
+    def forward(self, hidden_states, encoder_hidden_states=None, encoder_attention_mask=None):
+        """``encoder_attention_mask`` (B, T_kv) 0/1: key padding of the cross-attention (HF adds (1-mask) * finfo.min)."""
         kv = hidden_states if encoder_hidden_states is None else encoder_hidden_states
         B, Tq, _ = hidden_states.shape
         H, hd = self.num_attention_heads, self.attention_head_size
@@ -420,7 +421,8 @@ class QFormerAttention(nn.Module):
         v = self.value(kv).view(B, kv.shape[1], H, hd)
         if isinstance(self.q_norm, nn.LayerNorm):
             q, k = _ln(self.q_norm, q), _ln(self.k_norm, k)
-        return ops.attention(q.contiguous(), k.contiguous(), v.contiguous(), causal=False)   # scores / sqrt(hd), softmax, @ v
+        km = None if (encoder_attention_mask is None or encoder_hidden_states is None) else encoder_attention_mask.to(torch.uint8).contiguous()
+        return ops.attention(q.contiguous(), k.contiguous(), v.contiguous(), key_mask=km, causal=False)   # scores / sqrt(hd), softmax, @ v
 
 
 class _SelfOutput(nn.Module):
@@ -439,8 +441,8 @@ class _AttnBlock(nn.Module):
         self.attention = QFormerAttention(hidden, heads, kv_dim, eps, qk_norm)
         self.output = _SelfOutput(hidden, eps)
 
-    def forward(self, x, enc=None):
-        return self.output(self.attention(x, enc), x)
+    def forward(self, x, enc=None, enc_mask=None):
+        return self.output(self.attention(x, enc, enc_mask), x)
 
 
 class _Intermediate(nn.Module):
@@ -473,10 +475,10 @@ class QFormerLayer(nn.Module):
         self.intermediate_query = _Intermediate(cfg.hidden_size, cfg.intermediate_size)
         self.output_query = _Output(cfg.hidden_size, cfg.intermediate_size, cfg.layer_norm_eps)
 
-    def forward(self, x, enc):
+    def forward(self, x, enc, enc_mask=None):
         x = self.attention(x)
         if self.has_cross_attention:
-            x = self.crossattention(x, enc)
+            x = self.crossattention(x, enc, enc_mask)
         return self.output_query(self.intermediate_query(x), x)
 
 
@@ -495,10 +497,10 @@ class Blip2QFormerModel(nn.Module):
         self.layernorm = nn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
         self.encoder = _QFormerEncoder(cfg)
 
-    def forward(self, query_embeds, encoder_hidden_states):
+    def forward(self, query_embeds, encoder_hidden_states, encoder_attention_mask=None):
         x = _ln(self.layernorm, query_embeds)
         for layer in self.encoder.layer:
-            x = layer(x, encoder_hidden_states)
+            x = layer(x, encoder_hidden_states, encoder_attention_mask)
         return x
 
 
@@ -514,10 +516,10 @@ class PerceiverResampler(nn.Module):
         self.blip2qformer = Blip2QFormerModel(cfg)
         self.queries = nn.Parameter(torch.zeros(1, num_queries, hidden_size).normal_(0, 0.02))
 
-    def forward(self, encoder_hidden_states, query_embeds=None, **_):
+    def forward(self, encoder_hidden_states, query_embeds=None, encoder_attention_mask=None, **_):
         q = self.queries if query_embeds is None else query_embeds
         q = q.to(encoder_hidden_states.dtype).expand(encoder_hidden_states.shape[0], -1, -1)
-        return (self.blip2qformer(q, encoder_hidden_states),)
+        return (self.blip2qformer(q, encoder_hidden_states, encoder_attention_mask),)
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -334,9 +334,71 @@ def make_adapter(ref_ns):
     print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+# ---------------------------------------------------------------------------------------------------------
+# image-decoder glue: MMInterleaved._prepare_context_features_for_image_decoder / _prepare_mmfs_features_for_image_decoder
+# (mm_interleaved.py:254-340).  The module itself does not import under transformers 5.x, so the two method
+# definitions are lifted out of the reference FILE with ``ast`` at generation time and executed unmodified against a
+# stand-in ``self`` (special_token_dict, seq_len, context_feat_proj) -- nothing of the reference is stored here.
+# ---------------------------------------------------------------------------------------------------------
+IMGDEC_SOI, IMGDEC_SEQ_LEN, IMGDEC_C = 9, 40, 16
+
+
+def imgdec_inputs(seed=31):
+    g = torch.Generator().manual_seed(seed)
+    B, L = 3, 24
+    text_ids = torch.randint(10, 50, (B, L), generator=g)
+    text_ids[:, 0] = 1
+    for r, cols in enumerate([(2, 9, 17), (5,), (3, 20)]):           # <soi> positions per row: 3 + 1 + 2 = 6 images
+        for c in cols:
+            text_ids[r, c] = IMGDEC_SOI
+    n_img = 6
+    ctx = torch.randn((B, L, IMGDEC_C), generator=g)
+    feats = [torch.randn((n_img, 4, s, s), generator=g) for s in (8, 4, 2)]
+    w = torch.randn((IMGDEC_C, IMGDEC_C), generator=g) * 0.3
+    b = torch.randn((IMGDEC_C,), generator=g) * 0.1
+    nearest_bos = torch.tensor([0, 0, 12, 0, 0, 10])                   # second variant: explicit context starts
+    return text_ids, ctx, feats, w, b, nearest_bos
+
+
+def make_imgdec():
+    import ast
+    import types
+    ref_ns = ref_loader.load()
+    path = os.path.join(ref_loader.REF_ROOT, "mm_interleaved", "models", "mm_interleaved.py")
+    tree = ast.parse(open(path).read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "MMInterleaved")
+    wanted = {"_prepare_context_features_for_image_decoder", "_prepare_mmfs_features_for_image_decoder"}
+    fns = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    assert len(fns) == 2
+    mod = ast.Module(body=fns, type_ignores=[])
+    from typing import List, Optional
+    ns = dict(torch=torch, np=np, List=List, Optional=Optional,
+              get_1d_sincos_pos_embed_from_grid=ref_ns.pos_embed.get_1d_sincos_pos_embed_from_grid)
+    exec(compile(mod, path, "exec"), ns)
+    text_ids, ctx, feats, w, b, nearest_bos = imgdec_inputs()
+    proj = torch.nn.Linear(IMGDEC_C, IMGDEC_C)
+    with torch.no_grad():
+        proj.weight.copy_(w); proj.bias.copy_(b)
+    me = types.SimpleNamespace(special_token_dict=dict(soi_token_id=IMGDEC_SOI), seq_len=IMGDEC_SEQ_LEN, context_feat_proj=proj)
+    out = {}
+    with torch.no_grad():
+        for tag, nb in (("a", None), ("b", nearest_bos)):
+            cf, cm = ns["_prepare_context_features_for_image_decoder"](me, ctx, text_ids, None, None if nb is None else nb.clone())
+            mf, mm = ns["_prepare_mmfs_features_for_image_decoder"](me, feats, text_ids, None if nb is None else nb.clone(),
+                                                                   torch.tensor([3, 1, 2]))
+            out[f"ctx_{tag}"] = cf.numpy(); out[f"ctx_mask_{tag}"] = cm.numpy(); out[f"mmfs_mask_{tag}"] = mm.numpy()
+            for i, f in enumerate(mf):
+                out[f"mmfs_{tag}_{i}"] = f.numpy()
+    path = os.path.join(HERE, "imgdec_glue.npz")
+    np.savez_compressed(path, **out)
+    print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["msda", "mmfs", "llama", "mmfsnet", "adapter"]
+    which = sys.argv[1:] or ["msda", "mmfs", "llama", "mmfsnet", "adapter", "imgdec"]
+    if "imgdec" in which:
+        make_imgdec()
     if "adapter" in which:
         make_adapter(ref_loader.load())
     if "mmfsnet" in which:

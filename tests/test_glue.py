@@ -54,3 +54,49 @@ def test_feature_packing_matches_reference_loops():
     want = pack_mmfs_features_ref(feats, [8, 4, 2], nimg)
     got = pack_mmfs_features(feats, [8, 4, 2], nimg, 3)
     assert torch.equal(got, want)
+
+
+# ---- image-decoder glue (mm_interleaved.py:254-340): golden = the reference's own two methods run in the build container ----
+def _imgdec_golden():
+    import os
+
+    import numpy as np
+    from tests.golden.make_golden import IMGDEC_SEQ_LEN, IMGDEC_SOI, imgdec_inputs
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "imgdec_glue.npz"))
+    return z, imgdec_inputs(), IMGDEC_SOI, IMGDEC_SEQ_LEN
+
+
+def test_image_decoder_glue_oracle_pinned_to_reference_golden():
+    from oracle.glue import context_features_for_image_decoder_ref, mmfs_features_for_image_decoder_ref
+    z, (text_ids, ctx, feats, w, b, nearest_bos), soi, seq_len = _imgdec_golden()
+    for tag, nb in (("a", None), ("b", nearest_bos)):
+        cf, cm = context_features_for_image_decoder_ref(ctx, text_ids, soi, w, b, seq_len, nb)
+        assert torch.equal(cm, torch.from_numpy(z[f"ctx_mask_{tag}"]))
+        assert torch.equal(cf, torch.from_numpy(z[f"ctx_{tag}"]))                        # same ops, same order: bit-identical
+        mf, mm = mmfs_features_for_image_decoder_ref(feats, text_ids, soi, nb)
+        assert torch.equal(mm, torch.from_numpy(z[f"mmfs_mask_{tag}"]))
+        for i, f in enumerate(mf):
+            assert torch.equal(f, torch.from_numpy(z[f"mmfs_{tag}_{i}"]))
+
+
+def test_image_decoder_glue_vectorised_matches_reference_golden():
+    import mm_interleaved_b200.mm_interleaved as glue
+    z, (text_ids, ctx, feats, w, b, nearest_bos), soi, seq_len = _imgdec_golden()
+    proj = torch.nn.Linear(w.shape[1], w.shape[0])
+    with torch.no_grad():
+        proj.weight.copy_(w); proj.bias.copy_(b)
+    n_img = feats[0].shape[0]
+    for tag, nb in (("a", None), ("b", nearest_bos)):
+        with torch.no_grad():
+            cf, cm = glue.context_features_for_image_decoder(ctx, text_ids, soi, proj, seq_len, n_img, nb)
+        want = torch.from_numpy(z[f"ctx_{tag}"])
+        assert torch.equal(cm, torch.from_numpy(z[f"ctx_mask_{tag}"]))
+        assert cf.shape == want.shape and (cf - want).abs().max() <= 1e-6               # same linear on the same rows (batched GEMM order)
+        with torch.no_grad():   # static padding variant: longer L_max, same content under the mask
+            cf2, cm2 = glue.context_features_for_image_decoder(ctx, text_ids, soi, proj, seq_len, n_img, nb, pad_to=text_ids.shape[1])
+        L = want.shape[1]
+        assert (cf2[:, :L] - want).abs().max() <= 1e-6 and torch.equal(cm2[:, :L], cm) and int(cm2[:, L:].sum()) == 0
+        mf, mm = glue.mmfs_features_for_image_decoder(feats, text_ids, soi, nb)
+        assert torch.equal(mm, torch.from_numpy(z[f"mmfs_mask_{tag}"]))
+        for i, f in enumerate(mf):
+            assert torch.equal(f, torch.from_numpy(z[f"mmfs_{tag}_{i}"]))
