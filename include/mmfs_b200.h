@@ -188,6 +188,14 @@ int mmfs_attn_generic(const void *q, const void *k, const void *v, void *out, co
                       int B, int H, int Tq, int Tkv, int hd,
                       long q_bs, long q_ts, long k_bs, long k_ts, long v_bs, long v_ts, long o_bs, long o_ts,
                       float scale, int causal, int past, int dtype, void *stream);
+/* Single-query attention over a KV cache (the decode step of generate_texts, q_len = 1), split over the key range:
+ * q (B, 1, H, hd) with batch stride q_bs; k / v (B, Tkv, H, hd) views of the cache (row strides in elements, 16-byte
+ * aligned rows); out (B, 1, H, hd).  scratch: mmfs_attn_decode_scratch_floats(B, H, Tkv, hd) floats of device memory.
+ * causal != 0: the query sits at position `past` and sees keys 0..past.  f32 / f16 / bf16, hd % 32 == 0, hd <= 256. */
+long mmfs_attn_decode_scratch_floats(int B, int H, int Tkv, int hd);
+int mmfs_attn_decode(const void *q, const void *k, const void *v, void *out, const uint8_t *key_mask, float *scratch,
+                     int B, int H, int Tkv, int hd, long q_bs, long k_bs, long k_ts, long v_bs, long v_ts, long o_bs,
+                     float scale, int causal, int past, int dtype, void *stream);
 
 /*
  * softmax(q k^T * scale + mask) v on the tensor cores (tcgen05.mma, TMEM accumulators, TMA tiles):

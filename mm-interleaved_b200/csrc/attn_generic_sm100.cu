@@ -100,6 +100,161 @@ attn_generic_kernel(const T *__restrict__ q, const T *__restrict__ k, const T *_
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Decode (q_len = 1 over a KV cache): split-KV ("flash decoding").  The row-per-warp kernel above gives a decode step
+// B*H = 160 warps for the whole GPU, each walking 2k keys serially with scalar loads (3.4 ms per layer at the cfg-3
+// cache).  Here grid = (ceil(Tkv / 256), H, B): every CTA reduces 256 keys of one (b, h) -- lane = key for the
+// scores (16-byte loads along the key row, q broadcast from shared memory), lane = channels for P V (coalesced V
+// rows) -- and writes an (m, l, acc[hd]) partial; a second kernel merges the partials.  HBM-bound: K and V are read
+// exactly once.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kDecKeys = 256;     // keys per CTA
+constexpr int kDecWarps = 4;      // 64 keys per warp, two passes of 32
+
+template <typename T>
+__global__ void __launch_bounds__(32 * kDecWarps)
+attn_decode_split_kernel(const T *__restrict__ q, const T *__restrict__ k, const T *__restrict__ v,
+                         const uint8_t *__restrict__ key_mask, float *__restrict__ part, int H, int Tkv, int hd,
+                         long q_bs, long k_bs, long k_ts, long v_bs, long v_ts, float scale, int last_key) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    extern __shared__ float s_dec[];                  // q[hd] | per-warp partials [kDecWarps][hd + 2]
+    float *s_q = s_dec, *s_red = s_dec + hd;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z, n_split = gridDim.x;
+    const int cpl = hd / 32;                          // channels per lane in the P V phase (host: hd % 32 == 0, <= 8)
+    const T *qp = q + b * q_bs + (long)h * hd;
+    for (int d = threadIdx.x; d < hd; d += blockDim.x) s_q[d] = to_op(qp[d]) * scale;
+    __syncthreads();
+
+    float m_run = -INFINITY, l_run = 0.f;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    const int kbase = split * kDecKeys + warp * (kDecKeys / kDecWarps);
+#pragma unroll 1
+    for (int it = 0; it < kDecKeys / kDecWarps / 32; ++it) {
+        const int j0 = kbase + it * 32;
+        if (j0 > last_key) break;                     // warp-uniform
+        const int j = j0 + lane;
+        float sc = -INFINITY;
+        if (j <= last_key && (key_mask == nullptr || key_mask[(long)b * Tkv + j])) {
+            const T *kp = k + b * k_bs + (long)j * k_ts + (long)h * hd;
+            float dot = 0.f;
+            for (int d0 = 0; d0 < hd; d0 += VEC) {
+                float f[VEC];
+                Vec16<T>::unpack(ldg_nc_v4(kp + d0), f);
+#pragma unroll
+                for (int e = 0; e < VEC; e += 4) {
+                    const float4 qq = *reinterpret_cast<const float4 *>(s_q + d0 + e);
+                    dot = fmaf(f[e], qq.x, dot); dot = fmaf(f[e + 1], qq.y, dot);
+                    dot = fmaf(f[e + 2], qq.z, dot); dot = fmaf(f[e + 3], qq.w, dot);
+                }
+            }
+            sc = dot;
+        }
+        float cmax = sc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+        const float m_new = fmaxf(m_run, cmax);
+        if (m_new == -INFINITY) continue;             // nothing visible in this pass (warp-uniform)
+        const float corr = __expf(m_run - m_new);     // m_run = -inf -> 0
+        const float pj = __expf(sc - m_new);          // masked (-inf) -> 0
+        float psum = pj;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+        l_run = l_run * corr + psum;
+        m_run = m_new;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] *= corr;
+        const T *vb = v + b * v_bs + (long)h * hd + lane * cpl;
+        for (int jj = 0; jj < 32; ++jj) {
+            const float pw = __shfl_sync(0xffffffffu, pj, jj);
+            if (pw == 0.f) continue;                  // warp-uniform
+            const T *vp = vb + (long)(j0 + jj) * v_ts;
+            bool done = false;
+            if constexpr (sizeof(T) == 2) {
+                if (cpl == 4) {                        // hd = 128, 16-bit: one 8-byte load per lane, 256 B per warp
+                    const uint2 raw = *reinterpret_cast<const uint2 *>(vp);
+                    float f[8];
+                    Vec16<T>::unpack(make_uint4(raw.x, raw.y, 0u, 0u), f);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[c] = fmaf(pw, f[c], acc[c]);
+                    done = true;
+                } else if (cpl == 2) {                 // hd = 64
+                    const uint32_t raw = *reinterpret_cast<const uint32_t *>(vp);
+                    float f[8];
+                    Vec16<T>::unpack(make_uint4(raw, 0u, 0u, 0u), f);
+                    acc[0] = fmaf(pw, f[0], acc[0]); acc[1] = fmaf(pw, f[1], acc[1]);
+                    done = true;
+                }
+            }
+            if (!done) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c < cpl) acc[c] = fmaf(pw, to_op(vp[c]), acc[c]);
+            }
+        }
+    }
+    // merge the four warps of the CTA
+    float *mine = s_red + warp * (hd + 2);
+    if (lane == 0) { mine[hd] = m_run; mine[hd + 1] = l_run; }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        if (c < cpl) mine[lane * cpl + c] = acc[c];
+    __syncthreads();
+    float m_all = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < kDecWarps; ++w) m_all = fmaxf(m_all, s_red[w * (hd + 2) + hd]);
+    float *dst = part + (((long)b * H + h) * n_split + split) * (hd + 2);
+    for (int d = threadIdx.x; d < hd + 2; d += blockDim.x) {
+        float r = 0.f;
+        if (d == hd) r = m_all;
+        else if (m_all != -INFINITY) {
+#pragma unroll
+            for (int w = 0; w < kDecWarps; ++w) {
+                const float mw = s_red[w * (hd + 2) + hd];
+                if (mw != -INFINITY) r += __expf(mw - m_all) * s_red[w * (hd + 2) + (d < hd ? d : hd + 1)];
+            }
+        }
+        dst[d] = r;                                   // d < hd: acc; d == hd: m; d == hd + 1: l
+    }
+}
+
+template <typename T>
+__global__ void attn_decode_merge_kernel(const float *__restrict__ part, T *__restrict__ out, int H, int hd, int n_split,
+                                         long o_bs) {
+    const int h = blockIdx.x, b = blockIdx.y;
+    const float *p0 = part + (((long)b * H + h) * n_split) * (hd + 2);
+    float m = -INFINITY;
+    for (int s = 0; s < n_split; ++s) m = fmaxf(m, p0[s * (hd + 2) + hd]);
+    for (int d = threadIdx.x; d < hd; d += blockDim.x) {
+        float num = 0.f, den = 0.f;
+        if (m != -INFINITY)
+            for (int s = 0; s < n_split; ++s) {
+                const float ms = p0[s * (hd + 2) + hd];
+                if (ms == -INFINITY) continue;
+                const float w = __expf(ms - m);
+                num = fmaf(w, p0[s * (hd + 2) + d], num);
+                den = fmaf(w, p0[s * (hd + 2) + hd + 1], den);
+            }
+        out[b * o_bs + (long)h * hd + d] = from_op<T>(den > 0.f ? num / den : 0.f);   // fully masked row -> zeros
+    }
+}
+
+template <typename T>
+static int launch_attn_decode(const void *q, const void *k, const void *v, void *out, const uint8_t *key_mask, float *scratch,
+                              int B, int H, int Tkv, int hd, long q_bs, long k_bs, long k_ts, long v_bs, long v_ts, long o_bs,
+                              float scale, int last_key, cudaStream_t st) {
+    const int n_split = (last_key + kDecKeys) / kDecKeys;           // keys 0 .. last_key
+    dim3 grid(n_split, H, B);
+    const size_t smem = (size_t)(hd + kDecWarps * (hd + 2)) * sizeof(float);
+    attn_decode_split_kernel<T><<<grid, 32 * kDecWarps, smem, st>>>((const T *)q, (const T *)k, (const T *)v, key_mask, scratch, H,
+                                                                   Tkv, hd, q_bs, k_bs, k_ts, v_bs, v_ts, scale, last_key);
+    attn_decode_merge_kernel<T><<<dim3(H, B), hd < 128 ? 64 : 128, 0, st>>>(scratch, (T *)out, H, hd, n_split, o_bs);
+    MMFS_CUDA(cudaGetLastError());
+    return MMFS_OK;
+}
+
 template <typename T>
 static int launch_attn_generic(const void *q, const void *k, const void *v, void *out, const uint8_t *key_mask,
                                int B, int H, int Tq, int Tkv, int hd, long q_bs, long q_ts, long k_bs, long k_ts,
@@ -132,5 +287,32 @@ extern "C" int mmfs_attn_generic(const void *q, const void *k, const void *v, vo
         case MMFS_F16: return launch_attn_generic<__half>(q, k, v, out, key_mask, B, H, Tq, Tkv, hd, q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, o_bs, o_ts, scale, causal, past, st);
         case MMFS_BF16: return launch_attn_generic<__nv_bfloat16>(q, k, v, out, key_mask, B, H, Tq, Tkv, hd, q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, o_bs, o_ts, scale, causal, past, st);
         default: set_error("attn_generic: dtype %d unsupported", dtype); return MMFS_EINVAL;
+    }
+}
+
+extern "C" long mmfs_attn_decode_scratch_floats(int B, int H, int Tkv, int hd) {
+    return (long)B * H * ((Tkv + kDecKeys - 1) / kDecKeys) * (hd + 2);
+}
+
+extern "C" int mmfs_attn_decode(const void *q, const void *k, const void *v, void *out, const uint8_t *key_mask, float *scratch,
+                                int B, int H, int Tkv, int hd, long q_bs, long k_bs, long k_ts, long v_bs, long v_ts, long o_bs,
+                                float scale, int causal, int past, int dtype, void *stream) {
+    MMFS_CHECK_ARG(B >= 0 && H > 0 && Tkv > 0 && hd > 0, "attn_decode: bad shape");
+    if (B == 0) return MMFS_OK;
+    MMFS_CHECK_ARG(q && k && v && out && scratch, "attn_decode: null pointer argument");
+    const size_t es = dtype_size(dtype);
+    if (dtype == MMFS_F64 || es == 0 || hd % 32 != 0 || hd > 256 || B > 65535 || H > 65535 ||
+        ((uintptr_t)k | (uintptr_t)v) % 16 != 0 || (k_bs * es) % 16 != 0 || (k_ts * es) % 16 != 0 ||
+        (v_bs * es) % 16 != 0 || (v_ts * es) % 16 != 0 || (hd * es) % 16 != 0) {
+        set_error("attn_decode: needs f32/f16/bf16, hd %% 32 == 0 (<= 256), 16-byte aligned K / V rows");
+        return MMFS_EUNSUPPORTED;
+    }
+    const int last_key = causal ? (past < Tkv - 1 ? past : Tkv - 1) : Tkv - 1;     // the single query row sits at position `past`
+    MMFS_CHECK_ARG(last_key >= 0, "attn_decode: negative past");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case MMFS_F32: return launch_attn_decode<float>(q, k, v, out, key_mask, scratch, B, H, Tkv, hd, q_bs, k_bs, k_ts, v_bs, v_ts, o_bs, scale, last_key, st);
+        case MMFS_F16: return launch_attn_decode<__half>(q, k, v, out, key_mask, scratch, B, H, Tkv, hd, q_bs, k_bs, k_ts, v_bs, v_ts, o_bs, scale, last_key, st);
+        default: return launch_attn_decode<__nv_bfloat16>(q, k, v, out, key_mask, scratch, B, H, Tkv, hd, q_bs, k_bs, k_ts, v_bs, v_ts, o_bs, scale, last_key, st);
     }
 }

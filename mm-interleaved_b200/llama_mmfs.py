@@ -118,6 +118,19 @@ class LlamaMLP(nn.Module):
         return _addmm_residual(residual, act, self.down_proj.weight, inplace)
 
 
+class StaticKV:
+    """Pre-allocated key / value cache of one layer (extension): ``k``, ``v`` (B, T_max, H, hd) and the number of valid
+    positions.  Passing it as ``past_key_value`` makes the layer append IN PLACE instead of the reference's
+    ``torch.cat`` (modeling_llama_mmfs.py:236-239), which re-copies the whole cache of every layer for every token."""
+
+    __slots__ = ("k", "v", "length")
+
+    def __init__(self, batch, max_len, heads, head_dim, dtype, device):
+        self.k = torch.empty((batch, max_len, heads, head_dim), dtype=dtype, device=device)
+        self.v = torch.empty_like(self.k)
+        self.length = 0
+
+
 class LlamaAttention(nn.Module):
     def __init__(self, config: LlamaMMFSConfig):
         super().__init__()
@@ -153,15 +166,25 @@ class LlamaAttention(nn.Module):
         H, hd = self.num_heads, self.head_dim
         qkv = F.linear(hidden_states, self._qkv.get()).view(B, T, 3, H, hd)
         q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
-        past = 0 if past_key_value is None else past_key_value[0].shape[1]
+        static = isinstance(past_key_value, StaticKV)
+        past = 0 if past_key_value is None else (past_key_value.length if static else past_key_value[0].shape[1])
         if position_ids is None:
             position_ids = torch.arange(past, past + T, device=hidden_states.device)
         cos, sin = self.rope_tables(hidden_states.device, past + T)
         ops.rope_qk_(q, k, cos, sin, position_ids)
-        if past_key_value is not None:
-            k = torch.cat([past_key_value[0], k], dim=1)
-            v = torch.cat([past_key_value[1], v], dim=1)
-        present = (k, v) if use_cache else None
+        if static:
+            if past + T > past_key_value.k.shape[1]:
+                raise RuntimeError(f"StaticKV of {past_key_value.k.shape[1]} positions cannot take {past} + {T}")
+            past_key_value.k[:, past:past + T].copy_(k)
+            past_key_value.v[:, past:past + T].copy_(v)
+            past_key_value.length = past + T
+            k, v = past_key_value.k[:, :past + T], past_key_value.v[:, :past + T]
+            present = past_key_value
+        else:
+            if past_key_value is not None:
+                k = torch.cat([past_key_value[0], k], dim=1)
+                v = torch.cat([past_key_value[1], v], dim=1)
+            present = (k, v) if use_cache else None
         key_mask = None
         if attention_mask is not None:
             if attention_mask.dim() == 4:   # reference-style additive (B,1,T,T_kv): keys visible to the last query
@@ -290,6 +313,13 @@ class LlamaModel(nn.Module):
         self.norm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
         self.gradient_checkpointing = False
 
+    def static_cache(self, batch: int, max_len: int, dtype=None, device=None):
+        """One ``StaticKV`` per layer, to be passed as ``past_key_values`` (prefill with length 0, then decode)."""
+        p = self.embed_tokens.weight
+        H = self.config.num_attention_heads
+        return [StaticKV(batch, max_len, H, self.config.hidden_size // H, dtype or p.dtype, device or p.device)
+                for _ in self.layers]
+
     def get_input_embeddings(self):
         return self.embed_tokens
 
@@ -310,7 +340,10 @@ class LlamaModel(nn.Module):
         if inputs_embeds is None:
             inputs_embeds = self.embed_tokens(input_ids)
         B, T, _ = inputs_embeds.shape
-        past = 0 if past_key_values is None else past_key_values[0][0].shape[1]
+        if past_key_values is None:
+            past = 0
+        else:
+            past = past_key_values[0].length if isinstance(past_key_values[0], StaticKV) else past_key_values[0][0].shape[1]
         if position_ids is None:
             position_ids = torch.arange(past, past + T, dtype=torch.long, device=inputs_embeds.device)
         else:

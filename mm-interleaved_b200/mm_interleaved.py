@@ -264,7 +264,8 @@ class InterleavedForward(nn.Module):
 
     @torch.no_grad()
     def generate_texts(self, text_ids, visual_output, num_image_per_seq, max_num_image: int, attention_mask=None,
-                       max_new_tokens: int = 30, eos_token_id: Optional[int] = 2, pad_token_id: int = 0):
+                       max_new_tokens: int = 30, eos_token_id: Optional[int] = 2, pad_token_id: int = 0,
+                       static_cache: bool = True):
         """Greedy text continuation over the interleaved context -- the deterministic setting (num_beams=1,
         do_sample=False) of ``MMInterleaved.generate_texts`` (mm_interleaved.py:598-664), which drives HF ``generate``
         through ``CascadeLlamaForCausalLMWrapper`` (models/utils/causal_lm_cascade.py:91-204): prefill on
@@ -276,8 +277,11 @@ class InterleavedForward(nn.Module):
             attention_mask = torch.ones((B, L), dtype=torch.long, device=text_ids.device)
         mm_embeds, cross, feats = self.prepare(text_ids, visual_output, num_image_per_seq, max_num_image)
         position_ids = (attention_mask.long().cumsum(-1) - 1).clamp(min=0)
+        # pre-allocated per-layer caches appended in place (the reference's cat-per-token re-copies every layer's cache)
+        past = self.mm_decoder.static_cache(B, L + max_new_tokens, dtype=mm_embeds.dtype, device=mm_embeds.device) if static_cache else None
         out = self.mm_decoder(inputs_embeds=mm_embeds, attention_mask=attention_mask, position_ids=position_ids,
-                              vision_hidden_states=feats, cross_attention_mask=cross, use_cache=True, return_dict=True)
+                              past_key_values=past, vision_hidden_states=feats, cross_attention_mask=cross, use_cache=True,
+                              return_dict=True)
         past = out.past_key_values
         logits = self.text_decoder(out.last_hidden_state[:, -1:])
         new_ids = []

@@ -106,8 +106,22 @@ def attention(q, k, v, key_mask=None, causal=True, past=0, scale=None, force_gen
         km = key_mask.to(torch.uint8).contiguous()
         _require(tuple(km.shape) == (B, Tkv), "attention: key_mask must be (B, Tkv)")
     from . import attn_tc
+    es = q.element_size()
+    decode_ok = (Tq == 1 and not force_generic and q.dtype != torch.float64 and hd % 32 == 0 and hd <= 256 and
+                 (hd * es) % 16 == 0 and all(t.data_ptr() % 16 == 0 and (t.stride(0) * es) % 16 == 0 and
+                                            (t.stride(1) * es) % 16 == 0 for t in (k, v)))
     if not force_generic and attn_tc.supported(q, k, v, Tq, Tkv, hd):
         attn_tc.forward(q, k, v, out, km, causal, past, scale)
+    elif decode_ok:      # one query row over a KV cache: split-KV kernel (K and V read once, all SMs busy)
+        lib = _lib.lib()
+        scratch = torch.empty((lib.mmfs_attn_decode_scratch_floats(B, H, Tkv, hd),), dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            rc = lib.mmfs_attn_decode(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                      km.data_ptr() if km is not None else None, scratch.data_ptr(), B, H, Tkv, hd,
+                                      q.stride(0), k.stride(0), k.stride(1), v.stride(0), v.stride(1), out.stride(0), scale,
+                                      1 if causal else 0, int(past), _DTYPE_CODE[q.dtype], _stream())
+        _lib.check(rc, "attention (decode)")
+        launch_counter[0] += 1
     else:
         with torch.cuda.device(q.device):
             rc = _lib.lib().mmfs_attn_generic(

@@ -81,3 +81,41 @@ def test_unsupported_shapes_fall_to_the_bandwidth_kernel_and_errors_are_loud():
                                q.stride(0), q.stride(1), q.stride(0), q.stride(1), q.stride(0), q.stride(1), q.stride(0), q.stride(1),
                                0.1, 0, 0, _lib.BF16, None)
     assert rc == _lib.EUNSUPPORTED
+
+
+DECODE_CASES = [
+    # B, H, Tkv, T_cache, hd, masked
+    (3, 5, 700, 1024, 128, True),      # left-padded batch over a pre-allocated cache (views with a larger batch stride)
+    (2, 4, 2049, 2049, 128, False),    # cfg-3 decode step
+    (1, 3, 1, 8, 64, False),           # first token after a one-token prompt
+    (2, 2, 300, 300, 32, False),       # small head
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("case", range(len(DECODE_CASES)))
+def test_decode_attention_matches_eager(case, dtype):
+    """One query row over a KV cache (split-KV kernel) vs the fp32 eager statement; same tolerances as above, fp32: 1e-5."""
+    from mm_interleaved_b200 import ops
+    B, H, Tkv, Tc, hd, masked = DECODE_CASES[case]
+    g = torch.Generator().manual_seed(100 + case)
+    q = torch.randn((B, 1, H, hd), generator=g).to(dtype).to(DEV)
+    kc = torch.randn((B, Tc, H, hd), generator=g).to(dtype).to(DEV)
+    vc = torch.randn((B, Tc, H, hd), generator=g).to(dtype).to(DEV)
+    k, v = kc[:, :Tkv], vc[:, :Tkv]
+    km = None
+    if masked:
+        km = torch.ones((B, Tkv), dtype=torch.uint8, device=DEV)
+        km[0, :260] = 0                   # a whole 256-key split is masked
+        km[-1, 3:9] = 0
+    out = ops.attention(q, k, v, key_mask=km, causal=True, past=Tkv - 1).view(B, 1, H, hd)
+    ref = eager(q, k, v, km, True, Tkv - 1)
+    scale = ref.abs().max()
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert (out.float() - ref).abs().max() <= tol * scale
+    out_g = ops.attention(q, k, v, key_mask=km, causal=True, past=Tkv - 1, force_generic=True).view(B, 1, H, hd)
+    assert (out_g.float() - out.float()).abs().max() <= tol * scale
+    if masked:                            # a query whose keys are all masked returns zeros (DESIGN.md, attention masks)
+        km0 = km.clone(); km0[1] = 0
+        z = ops.attention(q, k, v, key_mask=km0, causal=True, past=Tkv - 1).view(B, 1, H, hd)
+        assert torch.count_nonzero(z[1]) == 0 and torch.isfinite(z.float()).all()

@@ -57,3 +57,8 @@ def test_greedy_generation_matches_oracle_loop():
         cur = torch.cat([cur, nxt[:, None]], dim=1)
     want = torch.stack(want, 1)
     assert torch.equal(got, want), (got, want)
+    # the reference-style growing (cat) cache gives the same tokens as the pre-allocated in-place cache used above
+    got_cat = dev.generate_texts(ids.cuda(), {"vis_embed": vis["vis_embed"].cuda(),
+                                              "multiscale_features": [f.cuda() for f in vis["multiscale_features"]]},
+                                 nimg.cuda(), 2, max_new_tokens=n_new, eos_token_id=None, static_cache=False).cpu()
+    assert torch.equal(got_cat, want)
