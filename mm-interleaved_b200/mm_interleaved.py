@@ -264,17 +264,24 @@ class InterleavedForward(nn.Module):
 
     @torch.no_grad()
     def generate_texts(self, text_ids, visual_output, num_image_per_seq, max_num_image: int, attention_mask=None,
-                       max_new_tokens: int = 30, eos_token_id: Optional[int] = 2, pad_token_id: int = 0,
-                       static_cache: bool = True):
-        """Greedy text continuation over the interleaved context -- the deterministic setting (num_beams=1,
-        do_sample=False) of ``MMInterleaved.generate_texts`` (mm_interleaved.py:598-664), which drives HF ``generate``
-        through ``CascadeLlamaForCausalLMWrapper`` (models/utils/causal_lm_cascade.py:91-204): prefill on
-        ``inputs_embeds`` with the image features, then one token per step over the KV cache, the last row of the
-        cross-attention mask serving every new token (mmfs.py:161-162), ``position_ids = cumsum(mask) - 1``
-        (causal_lm_cascade.py:179-185).  Batches are expected left-padded (collator.py:337).  Returns (B, n_new) ids."""
+                       max_new_tokens: int = 30, eos_token_id=2, pad_token_id: int = 0, static_cache: bool = True,
+                       min_length: int = 0, repetition_penalty: float = 1.0, use_nucleus_sampling: bool = False,
+                       top_p: float = 0.9, temperature: float = 1.0, generator: Optional[torch.Generator] = None):
+        """Text continuation over the interleaved context with one beam -- ``MMInterleaved.generate_texts``
+        (mm_interleaved.py:598-664), which drives HF ``generate`` through ``CascadeLlamaForCausalLMWrapper``
+        (models/utils/causal_lm_cascade.py:91-204): prefill on ``inputs_embeds`` with the image features, then one
+        token per step over the KV cache, the last row of the cross-attention mask serving every new token
+        (mmfs.py:161-162), ``position_ids = cumsum(mask) - 1`` (causal_lm_cascade.py:179-185).  Batches are expected
+        left-padded (collator.py:337).  Greedy by default (num_beams=1, do_sample=False: the release inference
+        config); the reference's other knobs that do not need beams are honoured with HF's semantics:
+        ``repetition_penalty`` (scores of already generated ids divided / multiplied), ``min_length`` (every eos id
+        is suppressed while fewer than ``min_length`` tokens were generated), several ``eos_token_id`` values (the
+        reference passes [eos, soi]), and ``use_nucleus_sampling`` = temperature + top-p sampling.  Beam search
+        (the reference's default num_beams=5 for captioning) is not implemented.  Returns (B, n_new) ids."""
         B, L = text_ids.shape
         if attention_mask is None:
             attention_mask = torch.ones((B, L), dtype=torch.long, device=text_ids.device)
+        eos_ids = [] if eos_token_id is None else ([int(eos_token_id)] if isinstance(eos_token_id, int) else [int(e) for e in eos_token_id])
         mm_embeds, cross, feats = self.prepare(text_ids, visual_output, num_image_per_seq, max_num_image)
         position_ids = (attention_mask.long().cumsum(-1) - 1).clamp(min=0)
         # pre-allocated per-layer caches appended in place (the reference's cat-per-token re-copies every layer's cache)
@@ -289,11 +296,27 @@ class InterleavedForward(nn.Module):
         mask = attention_mask
         last_cross = cross[:, -1:, :]
         pos = position_ids[:, -1:]
-        for _ in range(max_new_tokens):
-            nxt = logits[:, -1].argmax(-1)
-            if eos_token_id is not None:
+        for step_idx in range(max_new_tokens):
+            scores = logits[:, -1].float()
+            if repetition_penalty != 1.0 and new_ids:                    # HF RepetitionPenaltyLogitsProcessor
+                prev = torch.stack(new_ids, dim=1)
+                picked = scores.gather(1, prev)
+                scores = scores.scatter(1, prev, torch.where(picked < 0, picked * repetition_penalty, picked / repetition_penalty))
+            if step_idx < min_length and eos_ids:                        # HF MinLengthLogitsProcessor
+                scores[:, eos_ids] = float("-inf")
+            if use_nucleus_sampling:                                     # temperature, then top-p (HF warper order)
+                scores = scores / temperature
+                srt, idx = scores.sort(dim=-1, descending=False)
+                drop = srt.softmax(-1).cumsum(-1) <= (1.0 - top_p)
+                drop[:, -1] = False                                      # always keep the most likely token
+                scores = scores.masked_fill(drop.scatter(1, idx, drop), float("-inf"))
+                nxt = torch.multinomial(scores.softmax(-1), 1, generator=generator).squeeze(1)
+            else:
+                nxt = scores.argmax(-1)
+            if eos_ids:
                 nxt = torch.where(finished, torch.full_like(nxt, pad_token_id), nxt)
-                finished = finished | (nxt == eos_token_id)
+                for e in eos_ids:
+                    finished = finished | (nxt == e)
             new_ids.append(nxt)
             mask = torch.cat([mask, torch.ones((B, 1), dtype=mask.dtype, device=mask.device)], dim=1)
             pos = pos + 1

@@ -62,3 +62,86 @@ def test_greedy_generation_matches_oracle_loop():
                                               "multiscale_features": [f.cuda() for f in vis["multiscale_features"]]},
                                  nimg.cuda(), 2, max_new_tokens=n_new, eos_token_id=None, static_cache=False).cpu()
     assert torch.equal(got_cat, want)
+
+
+def _setup(seed_weights=31337):
+    import mm_interleaved_b200 as m
+    from mm_interleaved_b200.mm_interleaved import InterleavedForward
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = m.LlamaMMFSConfig(**LLAMA_TINY)
+    BOS, IMG, SOI = 1, 62, 63
+    model = InterleavedForward(cfg, special_tokens=dict(bos_token_id=BOS, image_token_id=IMG, soi_token_id=SOI), orig_vocab_size=62)
+    sd = seeded_state_dict(model.state_dict(), seed=seed_weights)
+    sd["text_decoder.head.weight"][60:] = 0
+    sd["text_decoder.head_new.weight"].zero_()
+    model.load_state_dict(sd)
+    g = torch.Generator().manual_seed(3)
+    L, n_tok = 20, 3
+    ids = torch.randint(3, 60, (2, L), generator=g)
+    ids[:, 0] = BOS
+    ids[0, 2] = SOI; ids[0, 3:3 + n_tok] = IMG
+    ids[0, 10] = SOI; ids[0, 11:11 + n_tok] = IMG
+    ids[1, 5] = SOI; ids[1, 6:6 + n_tok] = IMG
+    nimg = torch.tensor([2, 1])
+    vis = {"vis_embed": torch.randn((3, n_tok, cfg.hidden_size), generator=g) * 0.5,
+           "multiscale_features": [torch.randn((3, cfg.image_embed_dim, s, s), generator=g) for s in (8, 4, 2)]}
+    vis_d = {"vis_embed": vis["vis_embed"].cuda(), "multiscale_features": [f.cuda() for f in vis["multiscale_features"]]}
+    return cfg, model.cuda().eval(), sd, ids, nimg, vis, vis_d
+
+
+def _oracle_step_logits(cfg, sd, cur, ids, nimg, vis, step):
+    dec = {k[len("mm_decoder."):]: v for k, v in sd.items() if k.startswith("mm_decoder.")}
+    ocfg = dict(eps=cfg.rms_norm_eps, n_heads=cfg.num_attention_heads, n_layers=cfg.num_hidden_layers,
+                spatial_shapes=[(s, s) for s in cfg.spatial_shapes])
+    feats = pack_mmfs_features_ref(vis["multiscale_features"], cfg.spatial_shapes, nimg)
+    cross0 = cross_attention_mask_ref(ids, nimg, 1, 63)
+    emb = torch.nn.functional.embedding(cur, dec["embed_tokens.weight"])
+    emb = prepare_mm_embeds_ref(emb, cur, vis["vis_embed"], sd["soi_token"], 62, 63)
+    cross = torch.cat([cross0] + [cross0[:, -1:]] * step, dim=1)
+    hid, _ = llama_model_ref(dec, emb, torch.ones_like(cur), None, feats, cross, ocfg)
+    logits = hid[:, -1] @ sd["text_decoder.head.weight"].t()
+    logits[:, 62:] += hid[:, -1] @ sd["text_decoder.head_new.weight"].t()
+    return logits
+
+
+def test_min_length_eos_list_and_repetition_penalty_follow_hf_semantics():
+    """Greedy decoding with HF's RepetitionPenalty / MinLength processors and a list of eos ids, against the oracle
+    decoder loop with the same processors written out in plain PyTorch."""
+    cfg, dev, sd, ids, nimg, vis, vis_d = _setup()
+    n_new, min_len, pen, pad = 7, 3, 1.7, 0
+    free = dev.generate_texts(ids.cuda(), vis_d, nimg.cuda(), 2, max_new_tokens=n_new, eos_token_id=None).cpu()
+    eos = [int(free[0, 1]), int(free[1, 4])]          # ids the unconstrained run emits: they become end-of-sequence ids
+    got = dev.generate_texts(ids.cuda(), vis_d, nimg.cuda(), 2, max_new_tokens=n_new, eos_token_id=eos, pad_token_id=pad,
+                             min_length=min_len, repetition_penalty=pen).cpu()
+    cur, want, fin = ids.clone(), [], torch.zeros(2, dtype=torch.bool)
+    for step in range(n_new):
+        sc = _oracle_step_logits(cfg, sd, cur, ids, nimg, vis, step)
+        for b in range(2):
+            for t in set(int(x[b]) for x in want):                                   # repetition penalty on generated ids
+                sc[b, t] = sc[b, t] * pen if sc[b, t] < 0 else sc[b, t] / pen
+        if step < min_len:
+            sc[:, eos] = float("-inf")
+        nxt = sc.argmax(-1)
+        nxt = torch.where(fin, torch.full_like(nxt, pad), nxt)
+        for e in eos:
+            fin = fin | (nxt == e)
+        want.append(nxt)
+        cur = torch.cat([cur, nxt[:, None]], dim=1)
+    want = torch.stack(want, 1)
+    assert torch.equal(got, want), (got, want)
+    assert not torch.equal(got, free)                 # the processors changed the continuation
+
+
+def test_nucleus_sampling_limits_and_determinism():
+    cfg, dev, sd, ids, nimg, vis, vis_d = _setup()
+    args = (ids.cuda(), vis_d, nimg.cuda(), 2)
+    greedy = dev.generate_texts(*args, max_new_tokens=5, eos_token_id=None)
+    # top_p -> 0 keeps only the most likely token; temperature -> 0 concentrates all mass on it
+    a = dev.generate_texts(*args, max_new_tokens=5, eos_token_id=None, use_nucleus_sampling=True, top_p=1e-6)
+    b = dev.generate_texts(*args, max_new_tokens=5, eos_token_id=None, use_nucleus_sampling=True, top_p=1.0, temperature=1e-4)
+    assert torch.equal(a, greedy) and torch.equal(b, greedy)
+    g1 = torch.Generator(device="cuda").manual_seed(5)
+    g2 = torch.Generator(device="cuda").manual_seed(5)
+    s1 = dev.generate_texts(*args, max_new_tokens=6, eos_token_id=None, use_nucleus_sampling=True, top_p=0.95, temperature=2.0, generator=g1)
+    s2 = dev.generate_texts(*args, max_new_tokens=6, eos_token_id=None, use_nucleus_sampling=True, top_p=0.95, temperature=2.0, generator=g2)
+    assert torch.equal(s1, s2) and int(s1.max()) < 64 and not torch.equal(s1[:, :5], greedy)
