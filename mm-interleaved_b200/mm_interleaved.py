@@ -266,8 +266,9 @@ class InterleavedForward(nn.Module):
     def generate_texts(self, text_ids, visual_output, num_image_per_seq, max_num_image: int, attention_mask=None,
                        max_new_tokens: int = 30, eos_token_id=2, pad_token_id: int = 0, static_cache: bool = True,
                        min_length: int = 0, repetition_penalty: float = 1.0, use_nucleus_sampling: bool = False,
-                       top_p: float = 0.9, temperature: float = 1.0, generator: Optional[torch.Generator] = None):
-        """Text continuation over the interleaved context with one beam -- ``MMInterleaved.generate_texts``
+                       top_p: float = 0.9, temperature: float = 1.0, generator: Optional[torch.Generator] = None,
+                       num_beams: int = 1, length_penalty: float = 1.0, num_return_sequences: int = 1):
+        """Text continuation over the interleaved context -- ``MMInterleaved.generate_texts``
         (mm_interleaved.py:598-664), which drives HF ``generate`` through ``CascadeLlamaForCausalLMWrapper``
         (models/utils/causal_lm_cascade.py:91-204): prefill on ``inputs_embeds`` with the image features, then one
         token per step over the KV cache, the last row of the cross-attention mask serving every new token
@@ -276,8 +277,15 @@ class InterleavedForward(nn.Module):
         config); the reference's other knobs that do not need beams are honoured with HF's semantics:
         ``repetition_penalty`` (scores of already generated ids divided / multiplied), ``min_length`` (every eos id
         is suppressed while fewer than ``min_length`` tokens were generated), several ``eos_token_id`` values (the
-        reference passes [eos, soi]), and ``use_nucleus_sampling`` = temperature + top-p sampling.  Beam search
-        (the reference's default num_beams=5 for captioning) is not implemented.  Returns (B, n_new) ids."""
+        reference passes [eos, soi]), and ``use_nucleus_sampling`` = temperature + top-p sampling.  ``num_beams > 1``
+        runs HF-style beam search (``_beam_search`` below; the reference's captioning default is 5 beams) and returns
+        (B * num_return_sequences, <= max_new_tokens) padded ids; otherwise (B, max_new_tokens) ids."""
+        if num_beams > 1:
+            if use_nucleus_sampling:
+                raise NotImplementedError("beam-sample (num_beams > 1 with sampling) is not implemented")
+            return self._beam_search(text_ids, visual_output, num_image_per_seq, max_num_image, attention_mask, max_new_tokens,
+                                     eos_token_id, pad_token_id, min_length, repetition_penalty, num_beams, length_penalty,
+                                     num_return_sequences)
         B, L = text_ids.shape
         if attention_mask is None:
             attention_mask = torch.ones((B, L), dtype=torch.long, device=text_ids.device)
@@ -326,3 +334,116 @@ class InterleavedForward(nn.Module):
             past = step.past_key_values
             logits = self.text_decoder(step.last_hidden_state)
         return torch.stack(new_ids, dim=1)
+
+    @torch.no_grad()
+    def _beam_search(self, text_ids, visual_output, num_image_per_seq, max_num_image, attention_mask, max_new_tokens,
+                     eos_token_id, pad_token_id, min_length, repetition_penalty, num_beams, length_penalty, num_return):
+        """Beam search with the bookkeeping of HF ``GenerationMixin.beam_search`` + ``BeamSearchScorer`` (transformers
+        4.31, the version the reference pins; ``early_stopping=False``, one beam group): log-softmax scores, logits
+        processors on the log-probabilities, top 2*num_beams candidates per sequence, finished hypotheses ranked by
+        ``sum_logprobs / len(generated) ** length_penalty``, a sequence is done once ``num_beams`` hypotheses are all
+        at least as good as the best running beam could become.  The prompt is prefilled ONCE per sequence and its
+        cache rows are replicated per beam; every step re-gathers the cache rows by beam index (``_reorder_cache``)."""
+        from .llama_mmfs import StaticKV
+        B, L = text_ids.shape
+        nb, dev = num_beams, text_ids.device
+        if attention_mask is None:
+            attention_mask = torch.ones((B, L), dtype=torch.long, device=dev)
+        eos_ids = [] if eos_token_id is None else ([int(eos_token_id)] if isinstance(eos_token_id, int) else [int(e) for e in eos_token_id])
+        mm_embeds, cross, feats = self.prepare(text_ids, visual_output, num_image_per_seq, max_num_image)
+        position_ids = (attention_mask.long().cumsum(-1) - 1).clamp(min=0)
+        pre = self.mm_decoder.static_cache(B, L, dtype=mm_embeds.dtype, device=dev)
+        out = self.mm_decoder(inputs_embeds=mm_embeds, attention_mask=attention_mask, position_ids=position_ids,
+                              past_key_values=pre, vision_hidden_states=feats, cross_attention_mask=cross, use_cache=True,
+                              return_dict=True)
+        rep = torch.arange(B, device=dev).repeat_interleave(nb)                    # beam row -> sequence
+        past = self.mm_decoder.static_cache(B * nb, L + max_new_tokens, dtype=mm_embeds.dtype, device=dev)
+        for dst, src in zip(past, pre):
+            dst.k[:, :L].copy_(src.k.index_select(0, rep)); dst.v[:, :L].copy_(src.v.index_select(0, rep)); dst.length = L
+        del pre
+        logits = self.text_decoder(out.last_hidden_state[:, -1:]).index_select(0, rep)
+        feats_b, last_cross = feats.index_select(0, rep), cross[:, -1:, :].index_select(0, rep)
+        mask, pos = attention_mask.index_select(0, rep), position_ids[:, -1:].index_select(0, rep)
+
+        beam_scores = torch.zeros((B, nb), dtype=torch.float32, device=dev)
+        beam_scores[:, 1:] = -1e9
+        beam_scores = beam_scores.view(-1)
+        seqs = torch.zeros((B * nb, 0), dtype=torch.long, device=dev)              # generated ids per beam row
+        hyps = [[] for _ in range(B)]                                              # per sequence: (score, ids list)
+        worst = [1e9] * B
+        done = [False] * B
+
+        def add_hyp(b, ids, sum_logprobs):
+            score = sum_logprobs / (max(len(ids), 1) ** length_penalty)
+            if len(hyps[b]) < nb or score > worst[b]:
+                hyps[b].append((score, ids))
+                if len(hyps[b]) > nb:
+                    hyps[b].remove(min(hyps[b], key=lambda h: h[0]))
+                worst[b] = min(h[0] for h in hyps[b])
+
+        for step_idx in range(max_new_tokens):
+            scores = torch.log_softmax(logits[:, -1].float(), dim=-1)
+            if repetition_penalty != 1.0 and seqs.shape[1] > 0:
+                picked = scores.gather(1, seqs)
+                scores = scores.scatter(1, seqs, torch.where(picked < 0, picked * repetition_penalty, picked / repetition_penalty))
+            if step_idx < min_length and eos_ids:
+                scores[:, eos_ids] = float("-inf")
+            V = scores.shape[-1]
+            cand = (scores + beam_scores[:, None]).view(B, nb * V)
+            top_s, top_i = cand.topk(2 * nb, dim=1, largest=True, sorted=True)
+            top_s_h, top_i_h, seqs_h = top_s.tolist(), top_i.tolist(), seqs.tolist()   # one host round trip per step
+            cur_len = seqs.shape[1] + 1
+            nxt_scores = [[0.0] * nb for _ in range(B)]
+            nxt_tokens = [[pad_token_id] * nb for _ in range(B)]
+            nxt_rows = [[b * nb] * nb for b in range(B)]
+            for b in range(B):
+                if done[b]:
+                    continue
+                k = 0
+                for rank, (sc, idx) in enumerate(zip(top_s_h[b], top_i_h[b])):
+                    row, tok = b * nb + idx // V, idx % V
+                    if tok in eos_ids:
+                        if rank >= nb:
+                            continue
+                        add_hyp(b, seqs_h[row], sc)
+                    else:
+                        nxt_scores[b][k], nxt_tokens[b][k], nxt_rows[b][k] = sc, tok, row
+                        k += 1
+                    if k == nb:
+                        break
+                if len(hyps[b]) >= nb and worst[b] >= top_s_h[b][0] / (cur_len ** length_penalty):
+                    done[b] = True
+            beam_scores = torch.tensor(nxt_scores, dtype=torch.float32, device=dev).view(-1)
+            tok_t = torch.tensor(nxt_tokens, dtype=torch.long, device=dev).view(-1)
+            row_t = torch.tensor(nxt_rows, dtype=torch.long, device=dev).view(-1)
+            seqs = torch.cat([seqs.index_select(0, row_t), tok_t[:, None]], dim=1)
+            if all(done) or step_idx == max_new_tokens - 1:
+                break
+            for c in past:                                                        # _reorder_cache
+                n = c.length
+                c.k[:, :n].copy_(c.k.index_select(0, row_t)[:, :n]); c.v[:, :n].copy_(c.v.index_select(0, row_t)[:, :n])
+            mask = torch.cat([mask.index_select(0, row_t), torch.ones((B * nb, 1), dtype=mask.dtype, device=dev)], dim=1)
+            pos = pos.index_select(0, row_t) + 1
+            step = self.mm_decoder(inputs_embeds=self.mm_decoder.embed_tokens(tok_t[:, None]), attention_mask=mask, position_ids=pos,
+                                   past_key_values=past, vision_hidden_states=feats_b, cross_attention_mask=last_cross,
+                                   use_cache=True, return_dict=True)
+            logits = self.text_decoder(step.last_hidden_state)
+
+        # finalize: running beams of unfinished sequences become hypotheses; best `num_return` per sequence
+        seqs_h, bs_h = seqs.tolist(), beam_scores.tolist()
+        for b in range(B):
+            if not done[b]:
+                for j in range(nb):
+                    add_hyp(b, seqs_h[b * nb + j], bs_h[b * nb + j])
+        best = []
+        for b in range(B):
+            ranked = sorted(hyps[b], key=lambda h: h[0])
+            for _ in range(num_return):
+                best.append(ranked.pop()[1])
+        width = min(max(len(x) for x in best) + 1, max_new_tokens)
+        out_ids = torch.full((len(best), width), pad_token_id, dtype=torch.long)
+        for i, x in enumerate(best):
+            out_ids[i, :len(x)] = torch.tensor(x, dtype=torch.long)
+            if len(x) < width and eos_ids:
+                out_ids[i, len(x)] = eos_ids[0]
+        return out_ids.to(dev)

@@ -145,3 +145,88 @@ def test_nucleus_sampling_limits_and_determinism():
     s1 = dev.generate_texts(*args, max_new_tokens=6, eos_token_id=None, use_nucleus_sampling=True, top_p=0.95, temperature=2.0, generator=g1)
     s2 = dev.generate_texts(*args, max_new_tokens=6, eos_token_id=None, use_nucleus_sampling=True, top_p=0.95, temperature=2.0, generator=g2)
     assert torch.equal(s1, s2) and int(s1.max()) < 64 and not torch.equal(s1[:, :5], greedy)
+
+
+class _BeamHyps:
+    """BeamHypotheses of transformers 4.31 (generation/beam_search.py), early_stopping=False."""
+
+    def __init__(self, num_beams, length_penalty):
+        self.num_beams, self.length_penalty, self.beams, self.worst_score = num_beams, length_penalty, [], 1e9
+
+    def add(self, hyp, sum_logprobs):
+        score = sum_logprobs / (max(len(hyp), 1) ** self.length_penalty)
+        if len(self.beams) < self.num_beams or score > self.worst_score:
+            self.beams.append((score, hyp))
+            if len(self.beams) > self.num_beams:
+                srt = sorted((s, i) for i, (s, _) in enumerate(self.beams))
+                del self.beams[srt[0][1]]
+                self.worst_score = srt[1][0]
+            else:
+                self.worst_score = min(score, self.worst_score)
+
+    def is_done(self, best_sum_logprobs, cur_len):
+        if len(self.beams) < self.num_beams:
+            return False
+        return self.worst_score >= best_sum_logprobs / cur_len ** self.length_penalty
+
+
+def test_beam_search_matches_the_hf_algorithm_on_the_oracle_decoder():
+    """num_beams = 3 with min_length / eos list / length penalty: the GPU path (prefill once, replicated + re-gathered
+    in-place caches, split-KV decode attention) against HF's beam_search + BeamSearchScorer written out in plain
+    Python over the oracle decoder (full-prefix recompute per beam, no cache)."""
+    cfg, dev, sd, ids, nimg, vis, vis_d = _setup()
+    nb, n_new, min_len, lp, pad = 3, 6, 2, 1.3, 0
+    free = dev.generate_texts(ids.cuda(), vis_d, nimg.cuda(), 2, max_new_tokens=n_new, eos_token_id=None).cpu()
+    eos = [int(free[0, 3]), int(free[1, 2])]
+    got = dev.generate_texts(ids.cuda(), vis_d, nimg.cuda(), 2, max_new_tokens=n_new, eos_token_id=eos, pad_token_id=pad,
+                             min_length=min_len, num_beams=nb, length_penalty=lp).cpu()
+
+    B = ids.shape[0]
+    first = [0, int(nimg[0])]
+    rows = [b for b in range(B) for _ in range(nb)]
+    img_rows = [i for b in rows for i in range(first[b], first[b] + int(nimg[b]))]
+    ids_r, nimg_r = ids[rows], nimg[rows]
+    vis_r = {"vis_embed": vis["vis_embed"][img_rows], "multiscale_features": [f[img_rows] for f in vis["multiscale_features"]]}
+    seqs = [[] for _ in range(B * nb)]
+    beam_scores = torch.tensor([[0.0] + [-1e9] * (nb - 1)] * B).view(-1)
+    hyps = [_BeamHyps(nb, lp) for _ in range(B)]
+    done = [False] * B
+    for step in range(n_new):
+        cur = torch.cat([ids_r, torch.tensor(seqs, dtype=torch.long).view(B * nb, -1)], dim=1)
+        logp = torch.log_softmax(_oracle_step_logits(cfg, sd, cur, ids_r, nimg_r, vis_r, step).float(), -1)
+        if step < min_len:
+            logp[:, eos] = float("-inf")
+        V = logp.shape[-1]
+        top_s, top_i = (logp + beam_scores[:, None]).view(B, nb * V).topk(2 * nb, dim=1)
+        new_seqs, new_scores = [], []
+        for b in range(B):
+            if done[b]:
+                new_seqs += [seqs[b * nb] + [pad]] * nb; new_scores += [0.0] * nb
+                continue
+            kept = 0
+            for rank in range(2 * nb):
+                sc, idx = float(top_s[b, rank]), int(top_i[b, rank])
+                row, tok = b * nb + idx // V, idx % V
+                if tok in eos:
+                    if rank < nb:
+                        hyps[b].add(list(seqs[row]), sc)
+                else:
+                    new_seqs.append(seqs[row] + [tok]); new_scores.append(sc); kept += 1
+                if kept == nb:
+                    break
+            done[b] = done[b] or hyps[b].is_done(float(top_s[b].max()), len(seqs[b * nb]) + 1)
+        seqs, beam_scores = new_seqs, torch.tensor(new_scores)
+        if all(done):
+            break
+    for b in range(B):
+        if not done[b]:
+            for j in range(nb):
+                hyps[b].add(list(seqs[b * nb + j]), float(beam_scores[b * nb + j]))
+    best = [sorted(h.beams, key=lambda x: x[0])[-1][1] for h in hyps]
+    width = min(max(len(x) for x in best) + 1, n_new)
+    want = torch.full((B, width), pad, dtype=torch.long)
+    for i, x in enumerate(best):
+        want[i, :len(x)] = torch.tensor(x, dtype=torch.long)
+        if len(x) < width:
+            want[i, len(x)] = eos[0]
+    assert torch.equal(got, want), (got, want)
