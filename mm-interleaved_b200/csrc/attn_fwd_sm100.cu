@@ -29,14 +29,12 @@
 
 namespace mmfs {
 
-constexpr bool kPTmem = true;       // P goes back into S's own TMEM columns and feeds the second MMA as a TMEM A operand
-                                    // (false: the first-generation path, P staged in a swizzled shared-memory tile)
-constexpr int kBM = 128, kBN = 64;  // 64-key tiles: 112 KB of shared memory and 256 TMEM columns per CTA -> 2 CTAs / SM
+constexpr int kBM = 128, kBN = 64;  // 64-key tiles: 99 KB of shared memory (hd 128) and 256 TMEM columns per CTA -> 2 CTAs / SM
 constexpr int kAttnThreads = 192;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: softmax / epilogue
 constexpr uint32_t kTmemCols = 256; // S0 (64) | S1 (64) | O (<= 128)
 
 // Shared memory (dynamic, 1024-byte aligned):
-//   Q [HD/64 boxes][128 rows][128 B] | K [2 stages][HD/64][64][128 B] | V [2][HD/64][64][128 B] | P [128][128 B] |
+//   Q [HD/64 boxes][128 rows][128 B] | K [2 stages][HD/64][64][128 B] | V [2][HD/64][64][128 B] |
 //   barriers | tmem base | key-mask bytes [2][64]
 template <typename T, int HD>
 __global__ void __launch_bounds__(kAttnThreads, 2)
@@ -50,13 +48,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment; the dynamic window starts at offset 0 of the CTA's shared
     // memory (no static __shared__ in this kernel), which the __align__ above requests.  No slack is added on
-    // purpose: 2 CTAs of 115 KB must fit in 227 KB.
+    // purpose: 2 CTAs must fit in 227 KB.
     if ((s_addr(smem_raw) & 1023u) != 0u) { asm volatile("trap;"); }
     uint8_t *sQ = smem_raw;
     uint8_t *sK = sQ + Q_BYTES;
     uint8_t *sV = sK + 2 * KV_BYTES;
-    uint8_t *sP = sV + 2 * KV_BYTES;                       // absent (zero bytes) when P lives in TMEM
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + (kPTmem ? 0u : QBOX_BYTES));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sV + 2 * KV_BYTES);
     uint64_t *q_full = bars + 0, *k_full = bars + 1 /*[2]*/, *v_full = bars + 3 /*[2]*/, *k_empty = bars + 5 /*[2]*/,
              *v_empty = bars + 7 /*[2]*/, *s_full = bars + 9 /*[2]*/, *p_full = bars + 11, *o_ready = bars + 12;
     uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + 13);
@@ -144,11 +141,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     if (p.debug & 2) break;
                     // P: K-major, K = keys (one 64-key box).  V: MN-major, 16 key rows of 128 B per k-step,
                     // hd halves KBOX_BYTES apart (LBO)
-                    const uint64_t v_desc = smem_desc(s_addr(sV) + s * KV_BYTES + kk * 16 * 128, KBOX_BYTES, 1024);
-                    if (kPTmem)    // P_j sits in the first 32 columns of S buffer s: 16 keys = 8 columns per k-step
-                        umma_f16_ts(tmem_o, tmem_s0 + (uint32_t)s * kBN + kk * 8, v_desc, idesc_o, (j > 0) || (kk > 0));
-                    else
-                        umma_f16(tmem_o, smem_desc(s_addr(sP) + kk * 32, 16, 1024), v_desc, idesc_o, (j > 0) || (kk > 0));
+                    // P_j sits in the first 32 columns of S buffer s (TMEM A operand): 16 keys = 8 columns per k-step
+                    umma_f16_ts(tmem_o, tmem_s0 + (uint32_t)s * kBN + kk * 8,
+                                smem_desc(s_addr(sV) + s * KV_BYTES + kk * 16 * 128, KBOX_BYTES, 1024), idesc_o, (j > 0) || (kk > 0));
                 }
                 umma_commit(o_ready);
                 umma_commit(v_empty + s);
@@ -167,7 +162,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         float m_ref = -INFINITY, l_run = 0.f;
         const int causal_limit = p.causal ? (p.past + q_abs) : 0x7fffffff;   // last visible key index
         const int warp_causal_limit = p.causal ? (p.past + q0 + quarter * 32) : 0x7fffffff;   // ... of the warp's first row
-        uint8_t *p_row = sP + row * 128;
 
         for (int j = 0; j < n_tiles; ++j) {
             const int s = j & 1;
@@ -230,10 +224,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             const float l_tile = (la + lb) + (lc + ld);
             l_run = l_run * alpha + l_tile;
 
-            // O is rescaled only after the previous P V retired; with P in shared memory the same wait also protects
-            // the single P tile.  With P in TMEM the softmax of tile j never waits for P V_{j-1} otherwise.
+            // O is rescaled only after the previous P V retired; otherwise the softmax of tile j does not depend on it
+            // (P_j goes into S_j's own TMEM columns)
             const bool any_grow = __any_sync(0xffffffffu, grow) && (j > 0);
-            if (j > 0 && (!kPTmem || any_grow)) {
+            if (any_grow) {
                 bar_wait(o_ready, (j - 1) & 1);
                 tc_fence_after();
             }
@@ -247,20 +241,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     tmem_st32(tmem_o + lane_sel + c, o);
                 }
             }
-            if (kPTmem) {
-                tmem_st32_u32(tmem_s0 + (uint32_t)s * kBN + lane_sel, pk);   // row = lane, keys 2c, 2c+1 in column c
-                // protocol guard: P V(j-1) retired (it was issued a whole softmax earlier) before p_full moves on, so the
-                // MMA thread can never find this barrier two phases ahead of the one it waits for
-                if (j > 0 && !any_grow) bar_wait(o_ready, (j - 1) & 1);
-            } else {
-                // 64 keys = 128 B = 8 chunks of 16 B, chunk index XOR (row % 8): SWIZZLE_128B
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    const int phys = ch ^ (row & 7);
-                    *reinterpret_cast<uint4 *>(p_row + phys * 16) = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
-                }
-            }
-            if (!kPTmem) fence_async_smem();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
+            tmem_st32_u32(tmem_s0 + (uint32_t)s * kBN + lane_sel, pk);   // row = lane, keys 2c, 2c+1 in column c
+            // protocol guard: P V(j-1) retired (it was issued a whole softmax earlier) before p_full moves on, so the
+            // MMA thread can never find this barrier two phases ahead of the one it waits for
+            if (j > 0 && !any_grow) bar_wait(o_ready, (j - 1) & 1);
             tc_fence_before();
             bar_arrive(p_full);
         }
@@ -323,7 +307,7 @@ static int make_map(CUtensorMap *map, const void *ptr, int dtype, int B, int T, 
 
 template <typename T, int HD>
 static int launch_attn(const CUtensorMap &mq, const CUtensorMap &mk, const CUtensorMap &mv, const AttnParams &p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)(HD / 64) * (kBM * 128 + 4 * kBN * 128) + (kPTmem ? 0 : kBM * 128) + 14 * 8 + 2 * kBN + 16;
+    constexpr size_t smem = (size_t)(HD / 64) * (kBM * 128 + 4 * kBN * 128) + 14 * 8 + 2 * kBN + 16;
     auto kern = attn_fwd_kernel<T, HD>;
     static bool attr_set = false;
     if (!attr_set) {

@@ -219,8 +219,7 @@ msda_fwd_generic_kernel(const T *__restrict__ value, const int64_t *__restrict__
                         const T *__restrict__ attn, T *__restrict__ out,
                         long total, int S, int M, int D, int L, int Lq, int P, unsigned flags) {
     using OP = typename OpMath<T>::type;
-    const bool strict = flags & MMFS_MSDA_STRICT;
-    const bool w16 = flags & MMFS_MSDA_W16;
+    const bool strict = flags & MMFS_MSDA_STRICT;   // (MMFS_MSDA_W16 only affects the warp-per-row kernel)
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int c = (int)(idx % D);
         const long qm = idx / D;

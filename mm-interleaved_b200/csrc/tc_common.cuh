@@ -28,17 +28,6 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
         "bra W_%=;\n\t"
         "D_%=:\n\t}" ::"r"(s_addr(bar)), "r"(parity) : "memory");
 }
-// Warp-collective forms for warps whose 32 lanes all wait / arrive at the same point: one lane touches the mbarrier
-// (an arrive per lane is 32 serialised shared-memory atomics; 256 per tile made the barrier the attention kernel's
-// critical path), __syncwarp() orders the other lanes' accesses with it.
-__device__ __forceinline__ void bar_wait_warp(uint64_t *bar, uint32_t parity) {
-    if ((threadIdx.x & 31) == 0) bar_wait(bar, parity);
-    __syncwarp();
-}
-__device__ __forceinline__ void bar_arrive_warp(uint64_t *bar) {
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) bar_arrive(bar);
-}
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
@@ -89,14 +78,6 @@ __device__ __forceinline__ void tmem_st32_u32(uint32_t taddr, const uint32_t *v)
         "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
         "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
         "r"(v[30]), "r"(v[31])
-        : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_st16_u32(uint32_t taddr, const uint32_t *v) {   // 32 lanes x 16 columns
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::
-        "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
