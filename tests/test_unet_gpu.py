@@ -109,3 +109,24 @@ def test_geglu_matches_torch(dtype, tol):
     ref = h * torch.nn.functional.gelu(gate)
     err = (out.float().cpu() - ref).abs()
     assert out.shape == (3, 37, 1280) and (err <= tol * ref.abs().clamp_min(1.0)).all(), err.max().item()
+
+
+def test_graphed_denoise_loop_matches_eager():
+    """``denoise_loop(cuda_graph=True)`` (UNet evaluation captured once, replayed per step) gives the eager latents."""
+    import mm_interleaved_b200 as m
+    from mm_interleaved_b200 import unet_sd
+    torch.manual_seed(0)
+    unet = unet_sd.UNet2DConditionModel(block_out_channels=(320, 640), layers_per_block=1, attention_head_dim=(5, 10),
+                                        cross_attention_dim=128).to(DEV, torch.bfloat16).eval().to(memory_format=torch.channels_last)
+    net = m.MMFSNet(128, (320, 640), 1, downsample_factor=2, spatial_shapes=[32, 16, 8, 4]).to(DEV, torch.bfloat16).eval()
+    with torch.no_grad():
+        for blk in list(net.mmfs_down_blocks) + [net.mmfs_mid_block]:
+            blk.conv.weight.normal_(0, 0.2)
+    g = torch.Generator(device=DEV).manual_seed(2)
+    lat = torch.randn((2, 4, 32, 32), device=DEV, dtype=torch.bfloat16, generator=g)
+    cond = torch.randn((2, 7, 128), device=DEV, dtype=torch.bfloat16, generator=g)
+    feats = [torch.randn((2, 1, 128, s, s), device=DEV, dtype=torch.bfloat16, generator=g) for s in (32, 16, 8, 4)]
+    mask = torch.ones((2, 1), device=DEV)
+    a = unet_sd.denoise_loop(unet, lat, cond, torch.zeros_like(cond), feats, mask, net, num_steps=4, cuda_graph=False)
+    b = unet_sd.denoise_loop(unet, lat, cond, torch.zeros_like(cond), feats, mask, net, num_steps=4, cuda_graph=True)
+    assert torch.isfinite(a.float()).all() and (a.float() - b.float()).abs().max() <= 1e-2 * a.float().abs().max()
