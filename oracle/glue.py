@@ -51,48 +51,55 @@ def pack_mmfs_features_ref(multiscale_features, spatial_shapes, num_image_per_se
     return torch.cat(out, dim=2)
 
 
+def _soi_list(text_ids, soi_token_id):
+    """(row, column) of every <soi> token in row-major order."""
+    return [(r, c) for r in range(text_ids.shape[0]) for c in range(text_ids.shape[1]) if int(text_ids[r, c]) == soi_token_id]
+
+
 def context_features_for_image_decoder_ref(context_features, text_ids, soi_token_id, proj_weight, proj_bias, seq_len,
                                            nearest_bos_idxs=None):
-    """mm_interleaved.py:254-304, loop for loop (numpy table of utils/pos_embed.py:77-95)."""
+    """What mm_interleaved.py:254-304 produces, image by image and token by token: image i owns the decoder states from
+    its context start (``nearest_bos_idxs[i]``, default 0) to its <soi>, walked BACKWARDS from the <soi>; rows are
+    zero-padded to the longest context, projected (padding included) and offset by the 1-D sin-cos table
+    (utils/pos_embed.py:77-95) of the first L_max positions."""
+    import math
+    soi = _soi_list(text_ids, soi_token_id)
+    starts = [0] * len(soi) if nearest_bos_idxs is None else [int(v) for v in nearest_bos_idxs]
+    lens = [c - s0 + 1 for (_, c), s0 in zip(soi, starts)]
+    L_max, C = max(lens), context_features.shape[-1]
+    rows = torch.zeros((len(soi), L_max, C), dtype=context_features.dtype)
+    mask = torch.zeros((len(soi), L_max), dtype=torch.long)
+    for i, ((r, c), n) in enumerate(zip(soi, lens)):
+        for t in range(n):
+            rows[i, t] = context_features[r, c - t]
+            mask[i, t] = 1
+    half = C // 2
+    table = torch.zeros((L_max, C), dtype=torch.float32)
     import numpy as np
-    image_start_token_idx = (text_ids == soi_token_id).nonzero(as_tuple=True)[-1]
-    if nearest_bos_idxs is None:
-        nearest_bos_idxs = torch.zeros_like(image_start_token_idx)
-    row_ids = (text_ids == soi_token_id).nonzero(as_tuple=True)[0]
-    B_I, C = image_start_token_idx.shape[0], context_features.shape[-1]
-    lengths = image_start_token_idx - nearest_bos_idxs + 1
-    L_max = int(max(lengths))
-    per_image = torch.zeros((B_I, L_max, C)).type_as(context_features)
-    mask = torch.zeros((B_I, L_max)).type_as(image_start_token_idx)
-    for i in range(B_I):
-        f = context_features[row_ids[i], nearest_bos_idxs[i]: image_start_token_idx[i] + 1, :].flip(dims=(0,))
-        per_image[i, : lengths[i], :] = f
-        mask[i, : lengths[i]] = 1
-    omega = np.arange(C // 2, dtype=np.float32)
-    omega /= C / 2.0
-    omega = 1.0 / 10000 ** omega
-    out = np.einsum("m,d->md", np.arange(seq_len, dtype=np.float32), omega)
-    pos = torch.from_numpy(np.concatenate([np.sin(out), np.cos(out)], axis=1)).type_as(context_features)
-    per_image = torch.nn.functional.linear(per_image, proj_weight, proj_bias) + pos[None, :L_max]
-    return per_image, mask
+    omega = 1.0 / 10000 ** (np.arange(half, dtype=np.float32) / np.float32(C / 2.0))          # float32 like the numpy original
+    for pos in range(L_max):
+        ang = np.float32(pos) * omega
+        table[pos, :half] = torch.from_numpy(np.sin(ang))
+        table[pos, half:] = torch.from_numpy(np.cos(ang))
+    assert L_max <= seq_len and not math.isnan(float(table.sum()))
+    out = torch.nn.functional.linear(rows, proj_weight, proj_bias) + table.to(rows.dtype)[None]
+    return out, mask
 
 
 def mmfs_features_for_image_decoder_ref(multiscale_features, text_ids, soi_token_id, nearest_bos_idxs=None):
-    """mm_interleaved.py:306-340, loop for loop."""
+    """What mm_interleaved.py:306-340 produces: the lower-triangular mask restricted to the first sub-diagonal leaves one
+    candidate per image, its predecessor in row-major order, which counts iff its flattened <soi> position is not before
+    the image's own flattened context start."""
     L = text_ids.shape[1]
-    B_I = multiscale_features[0].shape[0]
-    ix, iy = (text_ids == soi_token_id).nonzero(as_tuple=True)
-    idx = ix * L + iy
-    if nearest_bos_idxs is None:
-        nearest_bos_idxs = torch.zeros_like(idx)
-    nb = ix * L + nearest_bos_idxs
-    m = nb[:, None] <= idx[None, :]
-    m = torch.triu(torch.tril(m, diagonal=-1), diagonal=-1)
-    feats = [torch.zeros_like(f)[:, None] for f in multiscale_features]
-    mask = torch.zeros((B_I, 1), dtype=torch.long)
-    for i in range(B_I):
-        sel = m[i].nonzero(as_tuple=True)[-1]
-        for src, dst in zip(multiscale_features, feats):
-            dst[i, : len(sel)] = src[sel]
-        mask[i, : len(sel)] = 1
+    soi = _soi_list(text_ids, soi_token_id)
+    n = len(soi)
+    starts = [0] * n if nearest_bos_idxs is None else [int(v) for v in nearest_bos_idxs]
+    feats = [torch.zeros((n, 1) + tuple(f.shape[1:]), dtype=f.dtype) for f in multiscale_features]
+    mask = torch.zeros((n, 1), dtype=torch.long)
+    for i in range(1, n):
+        (r, _), (pr, pc) = soi[i], soi[i - 1]
+        if r * L + starts[i] <= pr * L + pc:
+            for src, dst in zip(multiscale_features, feats):
+                dst[i, 0] = src[i - 1]
+            mask[i, 0] = 1
     return feats, mask
