@@ -100,3 +100,29 @@ def test_image_decoder_glue_vectorised_matches_reference_golden():
         assert torch.equal(mm, torch.from_numpy(z[f"mmfs_mask_{tag}"]))
         for i, f in enumerate(mf):
             assert torch.equal(f, torch.from_numpy(z[f"mmfs_{tag}_{i}"]))
+
+
+def test_sincos_1d_table_matches_the_reference_function():
+    """sincos_pos_embed_1d vs utils/pos_embed.py:77-95 imported from the reference tree (build container only)."""
+    import numpy as np
+    import pytest
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present (GPU box)")
+    import mm_interleaved_b200.mm_interleaved as glue
+    ref = ref_loader.load().pos_embed.get_1d_sincos_pos_embed_from_grid
+    for dim, n in ((16, 40), (5120, 7), (64, 2048)):
+        want = torch.from_numpy(ref(dim, np.arange(n, dtype=np.float32)))
+        got = glue.sincos_pos_embed_1d(dim, n)
+        assert got.shape == want.shape and torch.equal(got.to(want.dtype), want)
+
+
+def test_soi_positions_is_nonzero_in_row_major_order():
+    import mm_interleaved_b200.mm_interleaved as glue
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, 6, (5, 33), generator=g)
+    rows, cols = (ids == 3).nonzero(as_tuple=True)
+    r2, c2 = glue.soi_positions(ids, 3, rows.numel())
+    assert torch.equal(rows, r2) and torch.equal(cols, c2)
+    r3, c3 = glue.soi_positions(ids, 3, 4)                       # a static prefix of the list
+    assert torch.equal(rows[:4], r3) and torch.equal(cols[:4], c3)
