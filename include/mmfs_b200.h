@@ -45,6 +45,11 @@ extern "C" {
                                SASS FHFMA) -- fewer instructions per fetch; the reference keeps fp32 weights, so
                                this is opt-in (error << one storage ulp of the result) */
 
+/* flags for mmfs_sampler_forward (in addition to MMFS_MSDA_STRICT) */
+#define MMFS_SAMPLER_EXACT_WEIGHTS 4u /* keep fp32 tap weights in the specialised 16-bit kernel (default there: weights
+                                         rounded to the element type, FHFMA accumulate; bound in mmfs_sampler_v2_sm100.cu) */
+#define MMFS_SAMPLER_GENERIC       8u /* force the generic kernel (A/B runs, tests) */
+
 int mmfs_abi_version(void);
 const char *mmfs_last_error(void);
 
@@ -116,6 +121,9 @@ void mmfs_release_scratch(void);
 /* Tuning knobs (benchmarks / tests only): rows per warp per tile (0 = automatic); mapping bit 0 =
  * plain tile order instead of the per-SM swizzle. */
 int mmfs_msda_set_tuning(int rows_per_warp, int mapping);
+/* Same for the specialised fused sampler: rows per warp per tile (0 = automatic); wmode 1 = 16-bit tap weights +
+ * FHFMA (default), 0 = fp32 tap weights everywhere. */
+int mmfs_sampler_set_tuning(int rows_per_warp, int wmode);
 
 /*
  * Fused MMFS sampler: relpos-conditioned offsets / logits, image mask, null-slot softmax, sampling

@@ -20,4 +20,9 @@ from . import unet_sd, visual_tokenizer  # noqa: F401
 from .llama_mmfs import (LlamaAttention, LlamaDecoderLayer, LlamaMLP, LlamaMMFSAttention, LlamaMMFSConfig,  # noqa: F401
                          LlamaModel, LlamaRMSNorm)
 
-__version__ = "0.1.0"
+from .mm_interleaved import ImageDecoder, InterleavedForward, MMInterleaved, StableDiffusion, TextDecoder  # noqa: F401
+from .patch import (replace_all_b200, replace_llama_b200, replace_mmfs_b200, replace_msda_b200,  # noqa: F401
+                    replace_visual_b200)
+from ._cache import clear_activation_caches  # noqa: F401
+
+__version__ = "0.2.0"

@@ -15,6 +15,8 @@ OK, EINVAL, EUNSUPPORTED, ECUDA = 0, -1, -2, -3
 F32, F16, BF16, F64 = 0, 1, 2, 3
 MSDA_STRICT = 1
 MSDA_W16 = 2
+SAMPLER_EXACT_WEIGHTS = 4
+SAMPLER_GENERIC = 8
 
 _lib = None
 
@@ -31,6 +33,7 @@ SIGNATURES = {
     "mmfs_msda_forward_host": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _U, _P]),
     "mmfs_release_scratch": (None, []),
     "mmfs_msda_set_tuning": (_I, [_I, _I]),
+    "mmfs_sampler_set_tuning": (_I, [_I, _I]),
     "mmfs_sampler_forward": (_I, [_P] * 10 + [_I] * 13 + [_U, _P]),
     "mmfs_sampler_locw": (_I, [_P] * 10 + [_I] * 11 + [_P]),
     "mmfs_rmsnorm": (_I, [_P, _P, _P, _L, _I, _F, _I, _P]),

@@ -21,17 +21,21 @@ int cuda_fail(cudaError_t e, const char *what) {
     return MMFS_ECUDA;
 }
 
+int current_device() {
+    int dev = -1;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 int num_sms() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            cached = 148;  // B200
+    static int cached[kMaxDevices] = {};             // per device: a process may drive several GPUs
+    const int dev = current_device();
+    if (dev >= 0 && dev < kMaxDevices && cached[dev] > 0) return cached[dev];
+    int n = 0;
+    if (dev >= 0 && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
+        if (dev < kMaxDevices) cached[dev] = n;
+        return n;
     }
-    return cached;
+    return 148;  // B200
 }
 
 // per-thread device scratch for the host-buffer entry points

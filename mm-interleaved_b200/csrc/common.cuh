@@ -38,7 +38,9 @@ inline size_t dtype_size(int dtype) {
     }
 }
 
-int num_sms();
+int num_sms();            // of the CURRENT device
+int current_device();     // cudaGetDevice, -1 on failure
+constexpr int kMaxDevices = 64;
 
 // ---- element <-> opmath conversions ---------------------------------------------------
 template <typename T> struct OpMath { using type = float; };

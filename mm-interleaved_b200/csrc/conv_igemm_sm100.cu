@@ -212,12 +212,20 @@ extern "C" int mmfs_conv2d_nhwc(const void *x, const void *w, const void *bias, 
     dim3 grid((unsigned)(p.tiles_w * p.tiles_h * (B / TB)), (unsigned)(Cout / kConvBN));
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MMFS_BF16) {
-        static bool attr = false;
-        if (!attr) { MMFS_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        static bool attr[kMaxDevices] = {};            // the attribute is per device
+        const int dev = current_device();
+        if (dev < 0 || dev >= kMaxDevices || !attr[dev]) {
+            MMFS_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < kMaxDevices) attr[dev] = true;
+        }
         conv_igemm_kernel<__nv_bfloat16><<<grid, kConvThreads, smem, st>>>(mx, mw, p);
     } else {
-        static bool attr = false;
-        if (!attr) { MMFS_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        static bool attr[kMaxDevices] = {};
+        const int dev = current_device();
+        if (dev < 0 || dev >= kMaxDevices || !attr[dev]) {
+            MMFS_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < kMaxDevices) attr[dev] = true;
+        }
         conv_igemm_kernel<__half><<<grid, kConvThreads, smem, st>>>(mx, mw, p);
     }
     MMFS_CUDA(cudaGetLastError());

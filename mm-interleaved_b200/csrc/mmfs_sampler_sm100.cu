@@ -30,37 +30,6 @@
 
 namespace mmfs {
 
-template <typename T> __device__ __forceinline__ float round_to(float x) { return to_op(from_op<T>(x)); }
-template <> __device__ __forceinline__ float round_to<float>(float x) { return x; }
-
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-struct SamplerArgs {
-    const void *value;
-    const int64_t *shapes, *starts;
-    const void *qproj, *rtable;
-    const uint8_t *relpos;
-    const float *refpts, *scale_ratios;
-    void *out;
-    float *null_mass;
-    void *loc_out, *attn_out;
-    int S, M, n_img, n_lvl, Lq, P, Lq_r, Nr, Lr, R;
-    float null_logit;
-    unsigned flags;
-    int rows_per_warp, qtiles;
-    long ntiles;
-    int ctas_per_sm, nsm, swizzle;
-};
-
 // Shared memory of one CTA: int4 lvl[L] | float scale[n_lvl] (padded to 16 B) | per warp:
 //   Tap taps[kTapsPerWarp] | float xs[n_img*n_lvl*P] (logits of the row) | int vis[32]
 template <typename T, int D, bool EMIT>
@@ -78,7 +47,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, 3) mmfs_sampler_kernel(cons
     const int xs_elems = n_img * ((n_lvl * P + 31) / 32) * 32;
     const int q_elems = P * 2 + n_lvl * (P + 1);              // this head's slice of a qproj row: offsets | logits
     const int qs_elems = ((q_elems + 3) / 4) * 4;
-    const int per_warp_bytes = kTapsPerWarp * (int)sizeof(Tap) + (xs_elems + qs_elems) * 4 + 128;
+    const int per_warp_bytes = kTapsPerWarp * (int)sizeof(Tap) + (xs_elems + qs_elems) * 4 + 256;   // + s_vis[64]
     char *wbase = reinterpret_cast<char *>(s_dyn + L + scale_slots) + warp * per_warp_bytes;
     Tap *taps = reinterpret_cast<Tap *>(wbase);
     float *xs = reinterpret_cast<float *>(wbase + kTapsPerWarp * sizeof(Tap));
@@ -139,17 +108,23 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, 3) mmfs_sampler_kernel(cons
         for (int t = 0; t < kQPre; ++t)
             if (t < q_loads && lane + 32 * t < q_elems) qs[lane + 32 * t] = pre_q[t];
         const int r_mine = pre_r;
+        int r_mine1 = 0;                                      // images 32..63 (second ballot chunk, rare)
+        if (n_img > 32 && lane + 32 < n_img)
+            r_mine1 = a.relpos[((size_t)b * n_img + lane + 32) * a.Lq_r + (a.Lq_r == 1 ? 0 : q)];
         const RowCursor nxt = walk.next(cur);
         if (nxt.ok) prefetch(nxt);                            // loads for the next row are now in flight
 
         // ---- visible images of this token (mask row; last row if the mask is shorter) ---------
         const unsigned vis = __ballot_sync(0xffffffffu, r_mine != 0);
-        const int nvis = __popc(vis);
+        const unsigned vis1 = n_img > 32 ? __ballot_sync(0xffffffffu, r_mine1 != 0) : 0u;
+        const int nvis = __popc(vis) + __popc(vis1);
         // list of images to walk: the visible ones (EMIT: all, masked ones flagged by bit 30)
         if (EMIT) {
             if (lane < n_img) s_vis[lane] = lane | (r_mine << 8) | (r_mine == 0 ? (1 << 30) : 0);
-        } else if (r_mine != 0) {
-            s_vis[__popc(vis & ((1u << lane) - 1u))] = lane | (r_mine << 8);
+            if (lane + 32 < n_img) s_vis[lane + 32] = (lane + 32) | (r_mine1 << 8) | (r_mine1 == 0 ? (1 << 30) : 0);
+        } else {
+            if (r_mine != 0) s_vis[__popc(vis & ((1u << lane) - 1u))] = lane | (r_mine << 8);
+            if (r_mine1 != 0) s_vis[__popc(vis) + __popc(vis1 & ((1u << lane) - 1u))] = (lane + 32) | (r_mine1 << 8);
         }
         __syncwarp();
         const int nlist = EMIT ? n_img : nvis;
@@ -256,13 +231,14 @@ static int launch_sampler(SamplerArgs a, int N, cudaStream_t st) {
     const int qs_elems = ((a.P * 2 + a.n_lvl * (a.P + 1) + 3) / 4) * 4;
     if (a.P * 2 + a.n_lvl * (a.P + 1) > 128) { set_error("mmfs_sampler: P*2 + n_lvl*(P+1) > 128 unsupported"); return MMFS_EUNSUPPORTED; }
     const size_t smem = (size_t)(L + (a.n_lvl + 3) / 4) * sizeof(int4) +
-                        (size_t)kWarpsPerCta * (kTapsPerWarp * sizeof(Tap) + (size_t)(xs_elems + qs_elems) * 4 + 128);
+                        (size_t)kWarpsPerCta * (kTapsPerWarp * sizeof(Tap) + (size_t)(xs_elems + qs_elems) * 4 + 256);
     if (smem > 200 * 1024) { set_error("mmfs_sampler: n_img*n_lvl*P = %d too large", L * a.P); return MMFS_EUNSUPPORTED; }
     auto kern = mmfs_sampler_kernel<T, D, EMIT>;
-    static thread_local size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
+    static size_t smem_set[kMaxDevices] = {};  // per instantiation and per device
+    const int dev = current_device();
+    if (smem > 48 * 1024 && (dev < 0 || dev >= kMaxDevices || smem > smem_set[dev])) {
         MMFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+        if (dev >= 0 && dev < kMaxDevices) smem_set[dev] = smem;
     }
     int ctas_per_sm = 0;
     MMFS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 32 * kWarpsPerCta, smem));
@@ -307,8 +283,10 @@ static int sampler_entry(const void *value, const int64_t *shapes, const int64_t
     MMFS_CHECK_ARG(N >= 0 && Lq >= 0, "mmfs_sampler: negative batch or query count");
     MMFS_CHECK_ARG(S > 0 && M > 0 && D > 0 && n_img > 0 && n_lvl > 0 && P > 0 && R > 0,
                    "mmfs_sampler: non-positive dimension");
-    MMFS_CHECK_ARG(n_img <= 32, "mmfs_sampler: at most 32 images per sequence (got %d)", n_img);
+    MMFS_CHECK_ARG(n_img <= 64, "mmfs_sampler: at most 64 images per sequence (got %d)", n_img);
     MMFS_CHECK_ARG(R <= 256, "mmfs_sampler: relpos table too long (%d)", R);
+    MMFS_CHECK_ARG(n_img < R, "mmfs_sampler: relative image indices reach n_img = %d but the table has only %d rows "
+                   "(mmfs.py:177 asserts relpos < max_num_image_per_seq)", n_img, R);
     MMFS_CHECK_ARG((Lq_r == 1 || Lq_r == Lq) && (Nr == 1 || Nr == N) && (Lr == 1 || Lr == n_img * n_lvl),
                    "mmfs_sampler: broadcast dims must be 1 or full (Lq_r=%d Nr=%d Lr=%d)", Lq_r, Nr, Lr);
     MMFS_CHECK_ARG(dtype == MMFS_F32 || dtype == MMFS_F16 || dtype == MMFS_BF16, "mmfs_sampler: dtype %d unsupported", dtype);
@@ -328,6 +306,10 @@ static int sampler_entry(const void *value, const int64_t *shapes, const int64_t
     a.null_logit = -logf((float)(n_img * n_lvl));
     a.flags = flags;
     cudaStream_t st = (cudaStream_t)stream;
+    if (!emit && !(flags & MMFS_SAMPLER_GENERIC)) {   // the specialised kernel where its domain applies
+        const int rc = launch_sampler_v2(a, N, D, dtype, st);
+        if (rc != MMFS_EUNSUPPORTED) return rc;
+    }
     switch (dtype) {
         case MMFS_F32: return dispatch_sampler<float>(a, N, D, emit, st);
         case MMFS_F16: return dispatch_sampler<__half>(a, N, D, emit, st);

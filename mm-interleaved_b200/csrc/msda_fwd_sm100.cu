@@ -303,10 +303,11 @@ static int launch_rows(const void *value, const int64_t *shapes, const int64_t *
                         (size_t)kWarpsPerCta * (16 + 2 * (size_t)stage_elems * sizeof(T) + kTapsPerWarp * sizeof(Tap));
     if (smem > 200 * 1024) { set_error("msda: L*P = %d too large for the staging buffers", LP); return MMFS_EUNSUPPORTED; }
     auto kern = msda_fwd_rows_kernel<T, D>;
-    static thread_local size_t smem_set = 0;  // per (T, D) instantiation
-    if (smem > 48 * 1024 && smem > smem_set) {
+    static size_t smem_set[kMaxDevices] = {};  // per (T, D) instantiation and per device
+    const int dev = current_device();
+    if (smem > 48 * 1024 && (dev < 0 || dev >= kMaxDevices || smem > smem_set[dev])) {
         MMFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+        if (dev >= 0 && dev < kMaxDevices) smem_set[dev] = smem;
     }
     int ctas_per_sm = 0;
     MMFS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 32 * kWarpsPerCta, smem));

@@ -282,4 +282,46 @@ struct RowWalk {
     }
 };
 
+// ------------------------------------------------------------------------------------
+// Fused MMFS sampler: argument block + small numeric helpers shared by the generic kernel
+// (mmfs_sampler_sm100.cu) and the specialised P = 8 / D = 64 kernel (mmfs_sampler_v2_sm100.cu).
+// ------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float round_to(float x) { return to_op(from_op<T>(x)); }
+template <> __device__ __forceinline__ float round_to<float>(float x) { return x; }
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct SamplerArgs {
+    const void *value;
+    const int64_t *shapes, *starts;
+    const void *qproj, *rtable;
+    const uint8_t *relpos;
+    const float *refpts, *scale_ratios;
+    void *out;
+    float *null_mass;
+    void *loc_out, *attn_out;
+    int S, M, n_img, n_lvl, Lq, P, Lq_r, Nr, Lr, R;
+    float null_logit;
+    unsigned flags;
+    int rows_per_warp, qtiles;
+    long ntiles;
+    int ctas_per_sm, nsm, swizzle;
+};
+
+
+// Specialised fused sampler (16-bit element types, D = 64, P = 8, n_lvl in {3, 4}); returns MMFS_EUNSUPPORTED
+// without touching the error text when the configuration is outside its domain (the caller then takes the
+// generic kernel).
+int launch_sampler_v2(const SamplerArgs &a, int N, int D, int dtype, cudaStream_t st);
+int sampler_v2_set_tuning(int rows_per_warp, int wmode);
+
 }  // namespace mmfs

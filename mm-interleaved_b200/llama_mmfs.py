@@ -30,6 +30,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
+from ._cache import SourceCache
 from .mmfs import MMFS
 
 
@@ -212,7 +213,7 @@ class LlamaMMFSAttention(nn.Module):
                          spatial_shapes=config.spatial_shapes, max_num_image_per_seq=50)
         self.norm1 = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
         self.norm2 = LlamaRMSNorm(self.vision_hidden_size, eps=config.rms_norm_eps)
-        self._vision_cache = None   # (key, normalised vision features)
+        self._vision_cache = SourceCache()   # RMSNorm(vision features), identity-checked (see _cache.py)
         self._geom_cache = {}       # (device, n_img) -> (shapes, starts); (device, Lq) -> reference points
 
     def _geometry(self, device, n_img, hw, len_q):
@@ -241,11 +242,15 @@ class LlamaMMFSAttention(nn.Module):
 
     def forward(self, hidden_states, vision_hidden_states=None, cross_attention_mask=None, residual=None, inplace=False):
         h = self.norm1(hidden_states)
-        vkey = (vision_hidden_states.data_ptr(), tuple(vision_hidden_states.shape), vision_hidden_states._version,
-                self.norm2.weight._version)
-        if self._vision_cache is None or self._vision_cache[0] != vkey:
-            self._vision_cache = (vkey, self.norm2(vision_hidden_states))
-        v = self._vision_cache[1]
+        # RMSNorm(vision) depends only on the images: reuse it while the SAME tensor object is passed again (the decode
+        # steps of one generate call); modeling_llama_mmfs.py:353 recomputes it per layer per token
+        w2 = self.norm2.weight
+        vextra = (w2.data_ptr(), w2._version)
+        v = None if torch.is_grad_enabled() else self._vision_cache.get(vision_hidden_states, vextra)
+        if v is None:
+            v = self.norm2(vision_hidden_states)
+            if not torch.is_grad_enabled():
+                self._vision_cache.put(vision_hidden_states, v, vextra)
         _, n_img, hw, _ = v.shape
         shapes, starts, ref = self._geometry(h.device, n_img, hw, h.shape[1])
         if not torch.is_grad_enabled():

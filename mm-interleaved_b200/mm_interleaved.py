@@ -17,9 +17,9 @@ from torch import nn
 
 from .llama_mmfs import LlamaMMFSConfig, LlamaModel
 
-# special-token convention of the reference tokenizer (custom_datasets/wds_utils.py:186-215): the two
-# added ids follow the 32000 Llama ids
-DEFAULT_SPECIAL_TOKENS = dict(bos_token_id=1, image_token_id=32000, soi_token_id=32001)
+# special-token convention of the reference (mm_interleaved.py:33-39; custom_datasets/wds_utils.py:186-215 appends
+# "<|beginofimage|>" = 32000 and "<|image|>" = 32001 to the 32000 Llama ids)
+DEFAULT_SPECIAL_TOKENS = dict(bos_token_id=1, eos_token_id=2, pad_token_id=31999, soi_token_id=32000, image_token_id=32001)
 
 
 def splice_image_embeds(text_embeds, text_ids, image_embeds, soi_token, image_token_id, soi_token_id):
@@ -132,73 +132,167 @@ def mmfs_features_for_image_decoder(multiscale_features: Sequence[torch.Tensor],
     return feats, use.to(torch.long)[:, None]
 
 
-class TextHead(nn.Module):
-    """``TextDecoder`` (decoders/decoder_text.py): ``head`` over the original vocabulary plus ``head_new`` for the
-    added ids, summed on the tail columns (:155-157).  State-dict names match the reference."""
+class TextDecoder(nn.Module):
+    """``TextDecoder`` (decoders/decoder_text.py:26-163): ``head`` over the whole vocabulary plus ``head_new`` for the
+    added ids, summed on the tail columns (:155-157); both carry a bias (:43-46).  State-dict names match the reference.
+    ``forward`` keeps the reference signature (``inputs_embeds`` first, ``return_dict``); ``logits()`` is the plain
+    tensor-in / tensor-out form used inside this package."""
 
-    def __init__(self, hidden_size: int, vocab_size: int, orig_vocab_size: int):
+    def __init__(self, hidden_size: int = None, vocab_size: int = 32002, orig_vocab_size: int = 32000, config=None,
+                 txt_vocab_size: int = None, orig_txt_vocab_size: int = None, **_):
         super().__init__()
+        if config is not None and hidden_size is None:                  # reference keyword form (decoder_text.py:27-34)
+            hidden_size = config.hidden_size
+        vocab_size = txt_vocab_size if txt_vocab_size is not None else vocab_size
+        orig_vocab_size = orig_txt_vocab_size if orig_txt_vocab_size is not None else orig_vocab_size
+        assert 0 < orig_vocab_size < vocab_size
+        self.config = config
         self.orig_txt_vocab_size = orig_vocab_size
-        self.head = nn.Linear(hidden_size, vocab_size, bias=False)
-        self.head_new = nn.Linear(hidden_size, vocab_size - orig_vocab_size, bias=False)
+        self.head = nn.Linear(hidden_size, vocab_size, bias=True)
+        self.head_new = nn.Linear(hidden_size, vocab_size - orig_vocab_size, bias=True)
 
     _PAD = 128   # a vocabulary of 32002+ rows is not a multiple of 8: cuBLAS drops to an unaligned legacy kernel (5x slower)
 
-    def _fused_weight(self):
-        """head + head_new folded into one matrix, rows zero-padded to a multiple of 128 (inference only)."""
-        key = tuple((w.data_ptr(), w._version, w.dtype, w.device) for w in (self.head.weight, self.head_new.weight))
-        if getattr(self, "_fused", None) is None or self._fused[0] != key:
+    def _fused(self):
+        """head + head_new folded into one matrix / bias, rows zero-padded to a multiple of 128 (inference only)."""
+        ps = (self.head.weight, self.head_new.weight, self.head.bias, self.head_new.bias)
+        key = tuple((w.data_ptr(), w._version, w.dtype, w.device) for w in ps)
+        if getattr(self, "_fused_cache", None) is None or self._fused_cache[0] != key:
             V, C = self.head.weight.shape
             Vp = (V + self._PAD - 1) // self._PAD * self._PAD
-            w = self.head.weight.new_zeros((Vp, C))
-            w[:V] = self.head.weight.detach()
-            w[self.orig_txt_vocab_size:V] += self.head_new.weight.detach()
-            self._fused = (key, w)
-        return self._fused[1]
+            with torch.no_grad():
+                w = self.head.weight.new_zeros((Vp, C))
+                w[:V] = self.head.weight
+                w[self.orig_txt_vocab_size:V] += self.head_new.weight
+                b = self.head.bias.new_zeros((Vp,))
+                b[:V] = self.head.bias
+                b[self.orig_txt_vocab_size:V] += self.head_new.bias
+            self._fused_cache = (key, w, b)
+        return self._fused_cache[1], self._fused_cache[2]
 
-    def forward(self, hidden_states):
-        if torch.is_grad_enabled() and (self.head.weight.requires_grad or self.head_new.weight.requires_grad):
-            logits = self.head(hidden_states)
-            logits[..., self.orig_txt_vocab_size:] += self.head_new(hidden_states)
-            return logits
-        return F.linear(hidden_states, self._fused_weight())[..., :self.head.weight.shape[0]]
+    def logits(self, hidden_states):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            logits = self.head(hidden_states)                                              # :155-157 as written
+            tail = logits[..., self.orig_txt_vocab_size:] + self.head_new(hidden_states)
+            return torch.cat([logits[..., :self.orig_txt_vocab_size], tail], dim=-1)
+        w, b = self._fused()
+        return F.linear(hidden_states, w, b)[..., :self.head.weight.shape[0]]
+
+    def forward(self, inputs_embeds, attention_mask=None, position_ids=None, past_key_values=None, use_cache=None,
+                output_attentions=None, output_hidden_states=None, return_dict=None, **kwargs):
+        logits = self.logits(inputs_embeds)
+        if not return_dict:
+            return (logits,)
+        from types import SimpleNamespace
+        return SimpleNamespace(logits=logits, last_hidden_state=None, past_key_values=None, hidden_states=None,
+                               attentions=None)
+
+
+TextHead = TextDecoder   # round-1 name
+
+
+class StableDiffusion(nn.Module):
+    """``StableDiffusion`` (decoders/sd.py:23-218) on this repo's modules: ``unet`` (SD-2.1-base UNet with the patched
+    forward, unet_sd.py), ``mmfs_module`` (MMFSNet) and ``noise_scheduler`` (scheduler.py: DDPM on the SD-2.1-base
+    schedule, sd.py:48-50) -- same attribute / state-dict names as the reference.  The VAE is a diffusers object this
+    repository does not rebuild: ``vae_decode`` (a callable latents -> image in [-1, 1], e.g. ``AutoencoderKL.decode``)
+    may be attached; without it ``generate_images`` returns the denoised latents (the pipeline's
+    ``output_type="latent"`` result, sd.py:196-211)."""
+
+    def __init__(self, unet=None, mmfs_module=None, image_size=512, base_seed=0, use_random_seed=False,
+                 noise_scheduler=None, vae_decode=None, vae_scaling_factor=0.18215, **unet_kwargs):
+        super().__init__()
+        from . import unet_sd
+        from .scheduler import DDPMScheduler, SD21_BASE_SCHEDULER
+        self.unet = unet if unet is not None else unet_sd.UNet2DConditionModel(**unet_kwargs)
+        self.mmfs_module = mmfs_module
+        self.image_size, self.base_seed, self.use_random_seed = image_size, base_seed, use_random_seed
+        self.noise_scheduler = noise_scheduler if noise_scheduler is not None else DDPMScheduler(**SD21_BASE_SCHEDULER)
+        self.vae_decode, self.vae_scaling_factor = vae_decode, vae_scaling_factor
+
+    @torch.no_grad()
+    def generate_images(self, text_embeds, negative_prompt_embeds=None, num_validation_images=1, num_inference_steps=30,
+                        mini_bs=8, guidance_scale=7.5, mmfs_features=None, mmfs_mask=None, latents=None):
+        """sd.py:142-218: per validation image one generator seeded ``base_seed + num`` that draws the initial latents
+        AND the scheduler noise of every mini-batch in turn; mini-batches of ``mini_bs`` prompts through the CFG loop."""
+        import math
+        import numpy as np
+        from .unet_sd import denoise_loop
+        side = self.image_size // 8
+        outs = []
+        for num in range(num_validation_images):
+            seed = num + (int(np.random.randint(self.base_seed)) if self.use_random_seed else self.base_seed)
+            gen = torch.Generator(device=text_embeds.device).manual_seed(seed)
+            for it in range(math.ceil(text_embeds.shape[0] / mini_bs)):
+                sl = slice(it * mini_bs, it * mini_bs + mini_bs)
+                txt = text_embeds[sl]
+                neg = negative_prompt_embeds[sl] if negative_prompt_embeds is not None else torch.zeros_like(txt)
+                if latents is not None:
+                    lat = latents[sl]
+                else:
+                    lat = torch.randn((txt.shape[0], 4, side, side), generator=gen, device=txt.device, dtype=txt.dtype)
+                if lat.is_cuda:
+                    lat = lat.contiguous(memory_format=torch.channels_last)
+                lat = denoise_loop(self.unet, lat, txt, neg,
+                                   [f[sl] for f in mmfs_features] if mmfs_features is not None else None,
+                                   mmfs_mask[sl] if mmfs_mask is not None else None, self.mmfs_module,
+                                   num_steps=num_inference_steps, guidance=guidance_scale, scheduler=self.noise_scheduler,
+                                   generator=gen)
+                outs.append(lat)
+        lat = torch.cat(outs, dim=0)
+        if self.vae_decode is None:
+            return lat
+        image = self.vae_decode(lat.float() / self.vae_scaling_factor)                       # sd.py:212-215
+        return (image / 2 + 0.5).clamp(0, 1).float()
 
 
 class ImageDecoder(nn.Module):
-    """``ImageDecoder`` (decoders/decoder_image.py:9-156) on this repo's modules: ``perceiver_resampler`` (Q-Former, 77
-    queries of width 1024 over the per-image LLM context), ``neg_prompt_embeds`` and ``decoder`` = the SD UNet with
-    its MMFS network (decoders/sd.py:20-140).  The VAE and the noise scheduler are diffusers objects that are not part
-    of this repository: ``generate_images`` returns the denoised LATENTS (``output_type="latent"`` of the patched
-    pipeline, sd.py:196-211) and applies ``vae_decode`` if the caller supplies one."""
+    """``ImageDecoder`` (decoders/decoder_image.py:9-156): ``perceiver_resampler`` (Q-Former, 77 queries of width 1024
+    over the per-image LLM context), ``neg_prompt_embeds`` and ``decoder`` = ``StableDiffusion`` (UNet + MMFSNet +
+    scheduler).  State-dict names follow the reference (``decoder.unet.*``, ``decoder.mmfs_module.*``)."""
 
     def __init__(self, perceiver_config=None, seq_len=77, embed_dim=1024, unet=None, mmfs_module=None, image_size=512,
-                 base_seed=0):
+                 base_seed=0, sd_base_seed=None, sd_use_random_seed=False, mmfs_input_channel=1024, mmfs_feat_levels=4,
+                 uncond_prob=0.1, decoder: Optional[nn.Module] = None, **_):
         super().__init__()
         from .visual_tokenizer import PerceiverResampler
+        self.uncond_prob = uncond_prob
         self.perceiver_resampler = PerceiverResampler(**(perceiver_config or dict(num_queries=seq_len, hidden_size=embed_dim)))
         self.neg_prompt_embeds = nn.Parameter(torch.zeros(1, seq_len, embed_dim).normal_(0, 0.02))
-        self.unet, self.mmfs_module = unet, mmfs_module
-        self.image_size, self.base_seed = image_size, base_seed
+        if decoder is None:
+            if unet is None:            # full-size SD-2.1-base UNet + its MMFSNet (sd.py:58-82)
+                from . import unet_sd
+                from .sd_mmfs import MMFSNet
+                unet = unet_sd.UNet2DConditionModel()
+                mmfs_module = MMFSNet(mmfs_input_channel, tuple(unet.block_out_channels), 2,
+                                      downsample_factor=512 // image_size, n_levels=mmfs_feat_levels)
+            decoder = StableDiffusion(unet=unet, mmfs_module=mmfs_module, image_size=image_size,
+                                      base_seed=base_seed if sd_base_seed is None else sd_base_seed,
+                                      use_random_seed=sd_use_random_seed)
+        self.decoder = decoder
+
+    # round-1 attribute names
+    unet = property(lambda self: self.decoder.unet)
+    mmfs_module = property(lambda self: self.decoder.mmfs_module)
 
     @torch.no_grad()
-    def generate_images(self, context_features, context_attention_mask=None, mmfs_features=None, mmfs_mask=None,
-                        num_inference_steps=30, guidance_scale=7.5, latents=None, vae_decode=None, **_):
-        from .unet_sd import denoise_loop
+    def generate_images(self, context_features, context_attention_mask=None, mmfs_features=None, mmfs_mask=None, **kwargs):
+        """decoder_image.py:122-156.  Returns ``{"image": ...}`` (decoded images when the decoder has a VAE, else the
+        latents) and always ``{"latents": ...}`` when no VAE is attached."""
         text_embeds = self.perceiver_resampler(encoder_hidden_states=context_features,
-                                               encoder_attention_mask=context_attention_mask)[0]        # decoder_image.py:132-136
+                                               encoder_attention_mask=context_attention_mask)[0]        # :132-136
+        num_inference_steps = kwargs.pop("num_inference_steps", 30)
+        guidance_scale = kwargs.pop("guidance_scale", 7.5)
+        num_validation_images = kwargs.pop("num_validation_images", 1)
         neg = self.neg_prompt_embeds.to(text_embeds.dtype).expand_as(text_embeds)                       # :141-143
-        n = text_embeds.shape[0]
-        if latents is None:
-            g = torch.Generator(device=text_embeds.device).manual_seed(self.base_seed)                  # sd.py:166-169
-            side = self.image_size // 8
-            latents = torch.randn((n, 4, side, side), generator=g, device=text_embeds.device, dtype=text_embeds.dtype)
-        if latents.is_cuda:
-            latents = latents.contiguous(memory_format=torch.channels_last)
-        lat = denoise_loop(self.unet, latents, text_embeds, neg, mmfs_features, mmfs_mask, self.mmfs_module,
-                           num_steps=num_inference_steps, guidance=guidance_scale)
-        out = {"latents": lat}
-        if vae_decode is not None:                                                                      # sd.py:212-216
-            out["image"] = (vae_decode(lat.float() / 0.18215) / 2 + 0.5).clamp(0, 1)
+        res = self.decoder.generate_images(text_embeds=text_embeds, negative_prompt_embeds=neg,
+                                           num_validation_images=num_validation_images,
+                                           num_inference_steps=num_inference_steps, guidance_scale=guidance_scale,
+                                           mmfs_features=mmfs_features, mmfs_mask=mmfs_mask,
+                                           latents=kwargs.pop("latents", None))
+        out = {"image": res}
+        if self.decoder.vae_decode is None:
+            out["latents"] = res
         return out
 
 
@@ -213,7 +307,7 @@ class InterleavedForward(nn.Module):
         self.config = config
         self.special_token_dict = dict(DEFAULT_SPECIAL_TOKENS if special_tokens is None else special_tokens)
         self.mm_decoder = LlamaModel(config)
-        self.text_decoder = TextHead(config.hidden_size, config.vocab_size, orig_vocab_size)
+        self.text_decoder = TextDecoder(config.hidden_size, config.vocab_size, orig_vocab_size)
         self.soi_token = nn.Parameter(torch.zeros(1, config.hidden_size))
         self.spatial_shapes = list(config.spatial_shapes)
         self.context_feat_proj = nn.Linear(config.hidden_size, config.hidden_size)       # mm_interleaved.py:99
@@ -235,7 +329,7 @@ class InterleavedForward(nn.Module):
         mm_embeds, cross, feats = self.prepare(text_ids, visual_output, num_image_per_seq, max_num_image)
         out = self.mm_decoder(inputs_embeds=mm_embeds, attention_mask=attention_mask, vision_hidden_states=feats,
                               cross_attention_mask=cross, use_cache=False, return_dict=True)
-        return self.text_decoder(out.last_hidden_state)
+        return self.text_decoder.logits(out.last_hidden_state)
 
     @torch.no_grad()
     def generate_images(self, text_ids, visual_output, num_image_per_seq, max_num_image: int, attention_mask=None,
@@ -291,14 +385,14 @@ class InterleavedForward(nn.Module):
             attention_mask = torch.ones((B, L), dtype=torch.long, device=text_ids.device)
         eos_ids = [] if eos_token_id is None else ([int(eos_token_id)] if isinstance(eos_token_id, int) else [int(e) for e in eos_token_id])
         mm_embeds, cross, feats = self.prepare(text_ids, visual_output, num_image_per_seq, max_num_image)
-        position_ids = (attention_mask.long().cumsum(-1) - 1).clamp(min=0)
+        position_ids = (attention_mask.long().cumsum(-1) - 1).masked_fill(attention_mask == 0, 1)   # causal_lm_cascade.py:181-183
         # pre-allocated per-layer caches appended in place (the reference's cat-per-token re-copies every layer's cache)
         past = self.mm_decoder.static_cache(B, L + max_new_tokens, dtype=mm_embeds.dtype, device=mm_embeds.device) if static_cache else None
         out = self.mm_decoder(inputs_embeds=mm_embeds, attention_mask=attention_mask, position_ids=position_ids,
                               past_key_values=past, vision_hidden_states=feats, cross_attention_mask=cross, use_cache=True,
                               return_dict=True)
         past = out.past_key_values
-        logits = self.text_decoder(out.last_hidden_state[:, -1:])
+        logits = self.text_decoder.logits(out.last_hidden_state[:, -1:])
         new_ids = []
         finished = torch.zeros((B,), dtype=torch.bool, device=text_ids.device)
         mask = attention_mask
@@ -332,7 +426,7 @@ class InterleavedForward(nn.Module):
                                    position_ids=pos, past_key_values=past, vision_hidden_states=feats,
                                    cross_attention_mask=last_cross, use_cache=True, return_dict=True)
             past = step.past_key_values
-            logits = self.text_decoder(step.last_hidden_state)
+            logits = self.text_decoder.logits(step.last_hidden_state)
         return torch.stack(new_ids, dim=1)
 
     @torch.no_grad()
@@ -351,7 +445,7 @@ class InterleavedForward(nn.Module):
             attention_mask = torch.ones((B, L), dtype=torch.long, device=dev)
         eos_ids = [] if eos_token_id is None else ([int(eos_token_id)] if isinstance(eos_token_id, int) else [int(e) for e in eos_token_id])
         mm_embeds, cross, feats = self.prepare(text_ids, visual_output, num_image_per_seq, max_num_image)
-        position_ids = (attention_mask.long().cumsum(-1) - 1).clamp(min=0)
+        position_ids = (attention_mask.long().cumsum(-1) - 1).masked_fill(attention_mask == 0, 1)   # causal_lm_cascade.py:181-183
         pre = self.mm_decoder.static_cache(B, L, dtype=mm_embeds.dtype, device=dev)
         out = self.mm_decoder(inputs_embeds=mm_embeds, attention_mask=attention_mask, position_ids=position_ids,
                               past_key_values=pre, vision_hidden_states=feats, cross_attention_mask=cross, use_cache=True,
@@ -361,7 +455,7 @@ class InterleavedForward(nn.Module):
         for dst, src in zip(past, pre):
             dst.k[:, :L].copy_(src.k.index_select(0, rep)); dst.v[:, :L].copy_(src.v.index_select(0, rep)); dst.length = L
         del pre
-        logits = self.text_decoder(out.last_hidden_state[:, -1:]).index_select(0, rep)
+        logits = self.text_decoder.logits(out.last_hidden_state[:, -1:]).index_select(0, rep)
         feats_b, last_cross = feats.index_select(0, rep), cross[:, -1:, :].index_select(0, rep)
         mask, pos = attention_mask.index_select(0, rep), position_ids[:, -1:].index_select(0, rep)
 
@@ -427,7 +521,7 @@ class InterleavedForward(nn.Module):
             step = self.mm_decoder(inputs_embeds=self.mm_decoder.embed_tokens(tok_t[:, None]), attention_mask=mask, position_ids=pos,
                                    past_key_values=past, vision_hidden_states=feats_b, cross_attention_mask=last_cross,
                                    use_cache=True, return_dict=True)
-            logits = self.text_decoder(step.last_hidden_state)
+            logits = self.text_decoder.logits(step.last_hidden_state)
 
         # finalize: running beams of unfinished sequences become hypotheses; best `num_return` per sequence
         seqs_h, bs_h = seqs.tolist(), beam_scores.tolist()
@@ -447,3 +541,232 @@ class InterleavedForward(nn.Module):
             if len(x) < width and eos_ids:
                 out_ids[i, len(x)] = eos_ids[0]
         return out_ids.to(dev)
+
+
+def _llm_config_from(llm_config, llm_model_path, txt_vocab_size, image_embed_dim, cross_attention_frequency, spatial_shapes):
+    """``LlamaConfig.from_pretrained(llm_model_path)`` + the three MMFS additions (mm_interleaved.py:59-69) without
+    transformers: reads ``<llm_model_path>/config.json``.  Returns (LlamaMMFSConfig, original vocabulary size)."""
+    import dataclasses
+    import json
+    import os
+    if llm_config is None:
+        cfg_file = os.path.join(str(llm_model_path), "config.json")
+        if not os.path.exists(cfg_file):
+            raise FileNotFoundError(f"{cfg_file} not found: pass llm_model_path (a directory holding the Llama config.json) "
+                                    "or llm_config=LlamaMMFSConfig(...)")
+        raw = json.load(open(cfg_file))
+        names = {f.name for f in dataclasses.fields(LlamaMMFSConfig)}
+        llm_config = LlamaMMFSConfig(**{k: v for k, v in raw.items() if k in names})
+    elif isinstance(llm_config, dict):
+        llm_config = LlamaMMFSConfig(**llm_config)
+    else:
+        llm_config = dataclasses.replace(llm_config)
+    orig_vocab = llm_config.vocab_size if llm_config.vocab_size < txt_vocab_size else txt_vocab_size - 2
+    llm_config.vocab_size = txt_vocab_size                     # resize_token_embeddings (:72)
+    llm_config.image_embed_dim = image_embed_dim
+    llm_config.cross_attention_frequency = cross_attention_frequency
+    llm_config.spatial_shapes = list(spatial_shapes)
+    return llm_config, orig_vocab
+
+
+class MMInterleaved(InterleavedForward):
+    """The reference's top-level model surface (mm_interleaved/models/mm_interleaved.py:25-763) on this repo's modules:
+    same constructor keywords (:26-49), same sub-module / parameter names (``visual_tokenizer``, ``mm_decoder``,
+    ``text_decoder``, ``image_decoder``, ``context_feat_proj``, ``soi_token``), and the same entry points
+    ``forward(text_ids, image_tensors, ...)`` (:408-518), ``generate_texts`` (:598-664), ``generate_images`` (:520-596),
+    ``generate_scores`` (:666-743) and ``generate(mode, **batch)`` (:745-763) -- so ``inference.py`` / ``evaluate.py``
+    drive it with their unchanged batches (``model.generate(mode=..., **inputs)``, inference.py:237-269).
+
+    Differences a caller can see: weights are not fetched by the constructor (``llm_model_path`` is only read for its
+    ``config.json``; the reference's ``load_model_weights`` fills the parameters afterwards); ``forward`` computes the
+    text loss (and returns the logits) -- the image-decoder training loss needs the diffusers VAE and is not built;
+    ``generate_images`` returns latents as ``image`` unless a ``vae_decode`` callable is attached to
+    ``image_decoder.decoder``.  Extension keyword: ``llm_config`` (a ``LlamaMMFSConfig`` / dict) replaces
+    ``llm_model_path``; ``max_num_image`` in a batch skips the one host sync on ``num_image_per_seq.max()``."""
+
+    def __init__(self, *, llm_model_path="", seq_len=2048, txt_vocab_size=32002, loss_img_weight=10.0, loss_txt_weight=1.0,
+                 special_token_dict: Optional[dict] = None, visual_tokenizer_config=None, image_decoder_config=None,
+                 use_llama_gradient_checkpointing=True, num_img_token=64, image_embed_dim=1024, cross_attention_frequency=4,
+                 spatial_shapes=(32, 16, 8), dataset_to_ignore_noimage_cond_loss=(), llm_config=None,
+                 visual_tokenizer: Optional[nn.Module] = None, image_decoder: Optional[nn.Module] = None):
+        cfg, orig_vocab = _llm_config_from(llm_config, llm_model_path, txt_vocab_size, image_embed_dim,
+                                           cross_attention_frequency, spatial_shapes)
+        if image_decoder is None and image_decoder_config is not None:
+            image_decoder = ImageDecoder(**dict(image_decoder_config), mmfs_input_channel=image_embed_dim)
+        super().__init__(cfg, special_tokens=special_token_dict, orig_vocab_size=orig_vocab, seq_len=seq_len,
+                         image_decoder=image_decoder)
+        if visual_tokenizer is None:            # (extension: a pre-built module may be passed instead of its config)
+            from .visual_tokenizer import VisualTokenizer
+            visual_tokenizer = VisualTokenizer(llm_hidden_size=cfg.hidden_size, **dict(visual_tokenizer_config or {}))
+        self.visual_tokenizer = visual_tokenizer
+        self.txt_vocab_size = txt_vocab_size
+        self.loss_img_weight, self.loss_txt_weight = loss_img_weight, loss_txt_weight
+        self.num_img_token = num_img_token
+        self.dataset_to_ignore_noimage_cond_loss = list(dataset_to_ignore_noimage_cond_loss)
+        self.mm_decoder.gradient_checkpointing = use_llama_gradient_checkpointing      # inference: unused
+        self._tok_graph = None
+
+    # ---------------------------------------------------------------------------------------------------------
+    def enable_cuda_graphs(self, tokenizer: bool = True) -> "MMInterleaved":
+        """Replay the visual tokenizer (~2400 kernels of 5-50 us per 16 images) from a CUDA graph captured once per
+        image-batch shape.  Inference only; the tokenizer's outputs then live in static buffers that
+        the next call overwrites -- everything this class returns to the caller is cloned out of them."""
+        from ._graphs import GraphedCallable
+        self._tok_graph = GraphedCallable(self.visual_tokenizer) if tokenizer else None
+        return self
+
+    def _tokenize(self, image_tensors):
+        p = self.visual_tokenizer.proj.weight
+        image_tensors = image_tensors.to(device=p.device, dtype=p.dtype)
+        if self._tok_graph is not None and image_tensors.is_cuda and not torch.is_grad_enabled():
+            out = self._tok_graph(image_tensors)
+            return dict(out, _static=True)
+        return self.visual_tokenizer(image_tensors)
+
+    @staticmethod
+    def _owned(visual_output):
+        """The multi-scale maps as tensors the caller may keep (cloned when they alias CUDA-graph buffers)."""
+        ms = visual_output["multiscale_features"]
+        return [f.clone() for f in ms] if visual_output.get("_static") else ms
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _max_num_image(self, num_image_per_seq, max_num_image=None):
+        return int(max_num_image) if max_num_image is not None else int(num_image_per_seq.max())   # :194
+
+    def _prepare_mm_embeds(self, text_ids, image_tensors=None, num_image_per_seq=None, meta=None, max_num_image=None):
+        """mm_interleaved.py:121-183: tokenizer on the images, embed splice, visibility mask, MMFS feature packing."""
+        num_image_per_seq = num_image_per_seq.reshape(-1).to(text_ids.device)
+        visual_output = self._tokenize(image_tensors)
+        mm_embeds, cross, feats = self.prepare(text_ids, visual_output, num_image_per_seq,
+                                               self._max_num_image(num_image_per_seq, max_num_image))
+        return {"mm_embeds": mm_embeds, "cross_attention_mask": cross, "mmfs_features_mm": feats,
+                "multiscale_features": self._owned(visual_output), "_visual_output": visual_output}
+
+    def _prepare_gt_text_ids(self, text_ids, attention_mask=None, ignore_prompt_token_offset=0, gt_text_ids=None, meta=None):
+        """mm_interleaved.py:342-406 (next-token targets with prompt / pad / image / bos positions set to -100)."""
+        st = self.special_token_dict
+        if gt_text_ids is not None:
+            return gt_text_ids[..., 1:]
+        gt = text_ids.clone()
+        if isinstance(ignore_prompt_token_offset, int):
+            gt[:, :ignore_prompt_token_offset] = -100
+        else:
+            assert len(ignore_prompt_token_offset) == gt.shape[0]
+            for idx, offset in enumerate(ignore_prompt_token_offset):
+                gt[idx, :offset] = -100
+        if meta is not None and meta.get("dataset_name") in self.dataset_to_ignore_noimage_cond_loss:
+            pos = torch.arange(text_ids.shape[-1], device=text_ids.device)[None, :].expand_as(text_ids)
+            nearest_bos = pos.masked_fill(text_ids != st["bos_token_id"], -1).cummax(dim=1).values.clamp(min=0)
+            nearest_soi = pos.masked_fill(text_ids != st["soi_token_id"], -1).cummax(dim=1).values
+            gt = gt.masked_fill((nearest_soi < nearest_bos) | (nearest_soi == -1), -100)
+        gt = gt[:, 1:]
+        nxt = text_ids[:, 1:]
+        gt = gt.masked_fill(nxt == st["pad_token_id"], -100).masked_fill(nxt == st["image_token_id"], -100)
+        if attention_mask is not None:
+            gt = gt.masked_fill(attention_mask[:, 1:] == 0, -100)
+        bos2soi = (text_ids[:, :-1] == st["bos_token_id"]) & (nxt == st["soi_token_id"])
+        return gt.masked_fill(bos2soi, -100).masked_fill(nxt == st["bos_token_id"], -100)
+
+    def forward(self, text_ids, image_tensors=None, image_tensors_dec=None, num_image_per_seq=None, attention_mask=None,
+                gt_text_ids=None, nearest_bos_idxs=None, ignore_prompt_token_offset=0, loss_img_weight=None,
+                loss_txt_weight=None, meta=None, image_loss_mask=None, **kwargs):
+        """mm_interleaved.py:408-518 up to the text loss.  Returns ``loss_txt`` / ``loss`` like the reference plus
+        ``text_logits`` (B, T, V) (extension; ``return_loss=False`` stops there -- the "step" of SURVEY.md 8d).
+        Inference-only kernels: call under ``torch.no_grad()``."""
+        return_loss = kwargs.pop("return_loss", True)
+        out = self._prepare_mm_embeds(text_ids, image_tensors, num_image_per_seq, meta, kwargs.pop("max_num_image", None))
+        mm = self.mm_decoder(inputs_embeds=out.pop("mm_embeds"), attention_mask=attention_mask,
+                             vision_hidden_states=out.pop("mmfs_features_mm"),
+                             cross_attention_mask=out.pop("cross_attention_mask"), use_cache=False, return_dict=True)
+        out.pop("_visual_output")
+        logits = self.text_decoder.logits(mm.last_hidden_state)
+        if not return_loss:
+            out["text_logits"] = logits
+            return out
+        gt = self._prepare_gt_text_ids(text_ids, attention_mask, ignore_prompt_token_offset, gt_text_ids, meta)
+        loss_txt = F.cross_entropy(logits[:, :-1].float().transpose(1, 2), gt.contiguous(), reduction="mean")   # :458-463
+        w = self.loss_txt_weight if loss_txt_weight is None else loss_txt_weight
+        out.update(loss_txt=loss_txt.detach(), loss=loss_txt * w, text_logits=logits)
+        return out
+
+    @torch.no_grad()
+    def generate_texts(self, text_ids, image_tensors=None, num_image_per_seq=None, attention_mask=None, meta=None, **kwargs):
+        """mm_interleaved.py:598-664 with its BLIP-2 defaults (max_length 30, min_length 8, 5 beams, eos = [eos, soi])."""
+        st = self.special_token_dict
+        num_captions = kwargs.pop("num_captions", 1)
+        max_length = kwargs.pop("max_length", 30)
+        min_length = kwargs.pop("min_length", 8)
+        num_beams = kwargs.pop("num_beams", 5)
+        nucleus = kwargs.pop("use_nucleus_sampling", False)
+        top_p = kwargs.pop("top_p", 0.9)
+        repetition_penalty = kwargs.pop("repetition_penalty", 1.0)
+        length_penalty = kwargs.pop("length_penalty", 1.0)
+        temperature = kwargs.pop("temperature", 1)
+        num_image_per_seq = num_image_per_seq.reshape(-1).to(text_ids.device)
+        visual_output = self._tokenize(image_tensors)
+        ids = super().generate_texts(text_ids, visual_output, num_image_per_seq,
+                                     self._max_num_image(num_image_per_seq, kwargs.pop("max_num_image", None)),
+                                     attention_mask=attention_mask, max_new_tokens=max_length,
+                                     eos_token_id=[st.get("eos_token_id", 2), st["soi_token_id"]],
+                                     pad_token_id=st.get("pad_token_id", 0), min_length=min_length,
+                                     repetition_penalty=repetition_penalty, use_nucleus_sampling=nucleus, top_p=top_p,
+                                     temperature=temperature, generator=kwargs.pop("generator", None), num_beams=num_beams,
+                                     length_penalty=length_penalty, num_return_sequences=num_captions)
+        return {"multiscale_features": self._owned(visual_output), "text_ids": ids}
+
+    @torch.no_grad()
+    def generate_images(self, text_ids, image_tensors=None, num_image_per_seq=None, attention_mask=None, meta=None,
+                        target_image_idxs=None, **kwargs):
+        """mm_interleaved.py:520-596."""
+        num_image_per_seq = num_image_per_seq.reshape(-1).to(text_ids.device)
+        visual_output = self._tokenize(image_tensors)
+        return super().generate_images(text_ids, visual_output, num_image_per_seq,
+                                       self._max_num_image(num_image_per_seq, kwargs.pop("max_num_image", None)),
+                                       attention_mask=attention_mask, target_image_idxs=target_image_idxs, **kwargs)
+
+    @torch.no_grad()
+    def generate_scores(self, text_ids, image_tensors=None, num_image_per_seq=None, attention_mask=None, options_ids=None,
+                        options_attn_masks=None, **kwargs):
+        """mm_interleaved.py:666-743: for sample i, the log-likelihood of every answer option appended to its context,
+        summed over the option's unmasked tokens; mini-batches of 4 options.  The image of a sample is tokenised ONCE and
+        its outputs are expanded over the options (the reference re-encodes the same image per option row)."""
+        import math
+        scores = []
+        for i in range(len(text_ids)):
+            n_opt = options_ids[i].shape[0]
+            offset = len(text_ids[i])
+            ids = torch.cat((text_ids[i][None].expand(n_opt, -1), options_ids[i]), dim=1)
+            mask = torch.cat((attention_mask[i][None].expand(n_opt, -1), options_attn_masks[i]), dim=1)
+            vis1 = self._tokenize(image_tensors[[i]])
+            n_i = num_image_per_seq[[i]].reshape(-1).to(ids.device)
+            if int(n_i.numel()) != 1 or image_tensors[[i]].shape[0] != 1:
+                raise RuntimeError("generate_scores expects one image per sample (mm_interleaved.py:684-689)")
+            mini_bs = 4
+            chunks = []
+            for j in range(math.ceil(n_opt / mini_bs)):
+                sl = slice(j * mini_bs, (j + 1) * mini_bs)
+                nb = ids[sl].shape[0]
+                vis = {"vis_embed": vis1["vis_embed"].expand(nb, -1, -1),
+                       "multiscale_features": [f.expand(nb, -1, -1, -1) for f in vis1["multiscale_features"]]}
+                mm_embeds, cross, feats = self.prepare(ids[sl], vis, n_i.expand(nb), 1)
+                hid = self.mm_decoder(inputs_embeds=mm_embeds, attention_mask=mask[sl], vision_hidden_states=feats,
+                                      cross_attention_mask=cross, use_cache=False, return_dict=True).last_hidden_state
+                chunks.append(self.text_decoder.logits(hid[:, offset - 1:-1]))
+            logits = torch.cat(chunks)
+            assert logits.shape[1] == options_ids[i].shape[1]
+            logp = F.log_softmax(logits.float(), dim=-1).gather(-1, options_ids[i][..., None]).squeeze(-1)
+            scores.append((logp * options_attn_masks[i]).sum(dim=-1))
+        return {"scores": torch.stack(scores, dim=0)[:, None, :]}
+
+    def generate(self, mode="generate_images", **kwargs):
+        """mm_interleaved.py:745-763."""
+        if mode in ("generate_images", "generate_segm"):
+            assert self.image_decoder is not None
+            return self.generate_images(**kwargs)
+        if mode in ("generate_texts", "generate_vqa", "generate_grounding"):
+            assert self.text_decoder is not None
+            return self.generate_texts(**kwargs)
+        if mode == "generate_scores":
+            assert self.text_decoder is not None
+            return self.generate_scores(**kwargs)
+        raise NotImplementedError

@@ -28,6 +28,7 @@ from torch import nn
 
 from . import msda as _msda
 from . import sampler as _sampler
+from ._cache import SourceCache
 
 _FAST_HEAD_DIMS = (32, 64, 128)
 
@@ -95,7 +96,7 @@ class MMFS(nn.Module):
         self.query_relpos = nn.Embedding(max_num_image_per_seq, d_query)
         self._reset_parameters()
         self._fused = None        # (versions, W_cat, b_cat, rtable)
-        self._value_cache = None  # (key, value)
+        self._value_cache = SourceCache()  # value_proj(input_flatten), identity-checked (see _cache.py)
 
     def _reset_parameters(self):   # same initialisation scheme as mmfs.py:102-118
         grid = torch.empty(self.n_heads, 1, self.n_points, 2).uniform_(-self.offset_init_magnitude,
@@ -126,17 +127,20 @@ class MMFS(nn.Module):
 
     def project_value(self, input_flatten, input_padding_mask=None):
         """value_proj(input_flatten) as (N, n_img*hw, M, D), cached per input tensor (mmfs.py:165-172)."""
-        key = (input_flatten.data_ptr(), tuple(input_flatten.shape), input_flatten._version, input_flatten.dtype,
-               self.value_proj.weight._version, self.value_proj.weight.data_ptr(), input_padding_mask is None)
-        if input_padding_mask is None and self._value_cache is not None and self._value_cache[0] == key:
-            return self._value_cache[1]
+        w, b = self.value_proj.weight, self.value_proj.bias
+        extra = (w.data_ptr(), w._version, b.data_ptr(), b._version)
+        cacheable = input_padding_mask is None and not torch.is_grad_enabled()
+        if cacheable:
+            hit = self._value_cache.get(input_flatten, extra)
+            if hit is not None:
+                return hit
         N, n_img, hw, _ = input_flatten.shape
         value = self.value_proj(input_flatten)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.reshape(N, n_img * hw, self.n_heads, value.shape[-1] // self.n_heads).contiguous()
-        if input_padding_mask is None and not torch.is_grad_enabled():
-            self._value_cache = (key, value)
+        if cacheable:
+            self._value_cache.put(input_flatten, value, extra)
         return value
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
@@ -149,6 +153,11 @@ class MMFS(nn.Module):
         assert attention_mask.shape[-1] == n_images
         if input_spatial_shapes.shape[0] != n_images * self.n_levels:
             raise RuntimeError("input_spatial_shapes must list n_images * n_levels levels")
+        if n_images >= self.max_num_image_per_seq:
+            # the relative image index of a token reaches n_images and indexes query_relpos / the W e_r table; the
+            # reference asserts image_relpos.max() < max_num_image_per_seq (mmfs.py:177) after a device sync
+            raise RuntimeError(f"MMFS: {n_images} images per sequence need max_num_image_per_seq > {n_images} "
+                               f"(got {self.max_num_image_per_seq})")
         if reference_points.shape[-1] != 2:
             # the box form (mmfs.py:251-258) is not used by any caller on the interleaved forward path
             raise NotImplementedError("MMFS (B200): only 2-D reference points are implemented")
@@ -193,5 +202,5 @@ class MMFS(nn.Module):
     def _load_from_state_dict(self, *args, **kwargs):
         super()._load_from_state_dict(*args, **kwargs)
         self._fused = None
-        self._value_cache = None
+        self._value_cache.clear()
         self._ignore_nonzero = None

@@ -13,12 +13,20 @@ from .msda import _DTYPE_CODE, _require
 launch_counter = [0]   # kernels of ours launched through this module (bench.py's gpu_launches)
 
 
+def inference_only(name: str, *tensors) -> None:
+    """None of the ctypes kernels is autograd-aware: refuse to run where a gradient would be silently dropped."""
+    if torch.is_grad_enabled() and any(t is not None and torch.is_tensor(t) and t.requires_grad for t in tensors):
+        raise RuntimeError(f"{name}: this kernel is inference-only (no autograd support); call it under torch.no_grad() "
+                           "or detach its inputs / freeze its parameters")
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
 def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
     """LlamaRMSNorm.forward (decoders/modeling_llama_mmfs.py:53-70) over the last dim."""
+    inference_only("rmsnorm", x, weight)
     _require(x.is_cuda and x.is_contiguous() and weight.is_contiguous(), "rmsnorm: contiguous CUDA tensors required")
     _require(weight.dtype == x.dtype and weight.numel() == x.shape[-1], "rmsnorm: weight dtype / size mismatch")
     y = torch.empty_like(x)
@@ -32,6 +40,7 @@ def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
 
 
 def layernorm(x: torch.Tensor, weight, bias, eps: float) -> torch.Tensor:
+    inference_only("layernorm", x, weight, bias)
     _require(x.is_cuda and x.is_contiguous(), "layernorm: contiguous CUDA tensor required")
     y = torch.empty_like(x)
     rows = x.numel() // x.shape[-1]
@@ -48,6 +57,7 @@ def rope_qk_(q: torch.Tensor, k: torch.Tensor, cos: torch.Tensor, sin: torch.Ten
     """In-place rotary embedding of q and k, both (B, T, H, hd) views whose last two dims are dense
     (apply_rotary_pos_emb, decoders/modeling_llama_mmfs.py:165-172).  cos/sin: fp32 (max_pos, hd)."""
     B, T, H, hd = q.shape
+    inference_only("rope_qk_", q, k)
     _require(q.is_cuda and k.shape == q.shape and q.stride(3) == 1 and q.stride(2) == hd and k.stride(3) == 1
              and k.stride(2) == hd and q.stride(0) == T * q.stride(1) and k.stride(0) == T * k.stride(1),
              "rope_qk_: q / k must be (B,T,H,hd) with dense heads and uniform token stride")
@@ -65,6 +75,7 @@ def rope_qk_(q: torch.Tensor, k: torch.Tensor, cos: torch.Tensor, sin: torch.Ten
 
 def swiglu(gate_up: torch.Tensor) -> torch.Tensor:
     """act_fn(gate) * up on a (..., 2*I) tensor holding [gate | up] (LlamaMLP, :188-189)."""
+    inference_only("swiglu", gate_up)
     _require(gate_up.is_cuda and gate_up.is_contiguous() and gate_up.shape[-1] % 2 == 0, "swiglu: bad input")
     inter = gate_up.shape[-1] // 2
     out = torch.empty(gate_up.shape[:-1] + (inter,), dtype=gate_up.dtype, device=gate_up.device)
@@ -78,6 +89,7 @@ def swiglu(gate_up: torch.Tensor) -> torch.Tensor:
 
 def geglu(value_gate: torch.Tensor) -> torch.Tensor:
     """value * gelu(gate) (exact erf GELU) on a (..., 2*I) tensor holding [value | gate] (diffusers GEGLU)."""
+    inference_only("geglu", value_gate)
     _require(value_gate.is_cuda and value_gate.is_contiguous() and value_gate.shape[-1] % 2 == 0, "geglu: bad input")
     inter = value_gate.shape[-1] // 2
     out = torch.empty(value_gate.shape[:-1] + (inter,), dtype=value_gate.dtype, device=value_gate.device)
@@ -98,6 +110,7 @@ def attention(q, k, v, key_mask=None, causal=True, past=0, scale=None, force_gen
     Tkv = k.shape[1]
     for t in (q, k, v):
         _require(t.is_cuda and t.stride(3) == 1 and t.stride(2) == hd, "attention: heads must be dense (.., H, hd)")
+    inference_only("attention", q, k, v)
     _require(k.shape == v.shape and k.shape[0] == B and k.shape[2] == H and k.shape[3] == hd, "attention: k/v shape mismatch")
     scale = float(scale if scale is not None else hd ** -0.5)
     out = torch.empty((B, Tq, H, hd), dtype=q.dtype, device=q.device)
@@ -152,6 +165,7 @@ def conv2d(x: torch.Tensor, weight_khwc: torch.Tensor, bias=None, stride: int = 
     (B, Cout) broadcast over pixels, ``residual`` (like the output, channels_last)."""
     B, Cin, H, W = x.shape
     Cout, KH, KW, _ = weight_khwc.shape
+    inference_only("conv2d", x, weight_khwc, bias, add_bc, residual)
     _require(x.is_contiguous(memory_format=torch.channels_last) and weight_khwc.is_contiguous(), "conv2d: x must be channels_last")
     Ho, Wo = (H + 2 * padding - KH) // stride + 1, (W + 2 * padding - KW) // stride + 1
     out = torch.empty((B, Cout, Ho, Wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
@@ -179,6 +193,7 @@ def group_norm_supported(x: torch.Tensor) -> bool:
 def group_norm_nhwc(x: torch.Tensor, groups: int, weight=None, bias=None, eps: float = 1e-5, silu: bool = False) -> torch.Tensor:
     """``F.group_norm`` (+ ``F.silu`` when ``silu``) on a channels_last (B, C, H, W) tensor, result channels_last
     (torch's CUDA group_norm returns NCHW, which costs a layout round trip around each convolution)."""
+    inference_only("group_norm_nhwc", x, weight, bias)
     _require(group_norm_supported(x), "group_norm_nhwc: need a CUDA channels_last f32/f16/bf16 tensor with C % (16/size) == 0")
     B, C, H, W = x.shape
     y = torch.empty_like(x, memory_format=torch.channels_last)

@@ -27,9 +27,16 @@ def _common(shapes, starts, qproj, rtable, relpos, refpts, scale_ratios, M, n_lv
 
 
 def mmfs_sampler_forward(value, shapes, starts, qproj, rtable, relpos, refpts, scale_ratios,
-                         n_levels: int, n_points: int, want_null_mass: bool = False, strict: bool = False, w16: bool = False):
+                         n_levels: int, n_points: int, want_null_mass: bool = False, strict: bool = False, w16: bool = False,
+                         exact_weights: bool = False, generic: bool = False):
     """Fused relpos lookup + mask + null-slot softmax + location arithmetic + deformable gather.
-    Returns the sampled features (N, Lq, M*D) [and the null mass (N, Lq, M) fp32]."""
+    Returns the sampled features (N, Lq, M*D) [and the null mass (N, Lq, M) fp32].
+
+    16-bit tensors with D = 64, P = 8 and 3 or 4 levels run the specialised kernel (csrc/mmfs_sampler_v2_sm100.cu),
+    whose tap weights are rounded to the element type by default; ``exact_weights`` keeps them fp32 there,
+    ``generic`` forces the generic kernel (where ``w16`` is the opt-in for 16-bit weights)."""
+    from .ops import inference_only
+    inference_only("mmfs_sampler_forward", value, qproj, rtable)
     _require(value.is_cuda and value.is_contiguous() and value.dim() == 4, "value must be contiguous CUDA (N,S,M,D)")
     _, S, M, D = value.shape
     N, Lq, n_img = _common(shapes, starts, qproj, rtable, relpos, refpts, scale_ratios, M, n_levels, n_points)
@@ -44,7 +51,9 @@ def mmfs_sampler_forward(value, shapes, starts, qproj, rtable, relpos, refpts, s
             relpos.data_ptr(), refpts.data_ptr(), scale_ratios.data_ptr(), out.data_ptr(),
             null_mass.data_ptr() if want_null_mass else None,
             N, S, M, D, n_img, n_levels, Lq, n_points, relpos.shape[2], refpts.shape[0], refpts.shape[2],
-            rtable.shape[0], _DTYPE_CODE[value.dtype], (_lib.MSDA_STRICT if strict else 0) | (_lib.MSDA_W16 if w16 else 0),
+            rtable.shape[0], _DTYPE_CODE[value.dtype],
+            (_lib.MSDA_STRICT if strict else 0) | (_lib.MSDA_W16 if w16 else 0) |
+            (_lib.SAMPLER_EXACT_WEIGHTS if exact_weights else 0) | (_lib.SAMPLER_GENERIC if generic else 0),
             torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "mmfs_sampler_forward")
     return (out, null_mass) if want_null_mass else out
@@ -69,3 +78,8 @@ def mmfs_sampler_locw(shapes, starts, qproj, rtable, relpos, refpts, scale_ratio
             rtable.shape[0], _DTYPE_CODE[qproj.dtype], torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "mmfs_sampler_locw")
     return loc, attn, null_mass
+
+
+def set_sampler_tuning(rows_per_warp: int = 0, wmode: int = 1) -> None:
+    """Benchmarks / tests: rows per warp per tile (0 = automatic) and the weight mode of the specialised kernel."""
+    _lib.check(_lib.lib().mmfs_sampler_set_tuning(int(rows_per_warp), int(wmode)), "mmfs_sampler_set_tuning")

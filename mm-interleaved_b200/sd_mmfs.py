@@ -24,6 +24,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
+from ._cache import SourceCache
 from .mmfs import MMFS
 
 
@@ -95,7 +96,7 @@ class MMFSBlock(nn.Module):
         nn.init.zeros_(self.conv.weight)       # zero_module (:148-151)
         nn.init.zeros_(self.conv.bias)
         self._cache = {}
-        self._feat_cache = None
+        self._feat_cache = SourceCache()   # LayerNorm(ms_feat), identity-checked (see _cache.py)
         self._fused_out = None
 
     def _reset_parameters(self):
@@ -123,11 +124,14 @@ class MMFSBlock(nn.Module):
         return self._fused_out[1], self._fused_out[2]
 
     def normalised_features(self, ms_feat):
-        key = (ms_feat.data_ptr(), tuple(ms_feat.shape), ms_feat._version, self.feat_norm.weight._version)
-        if self._feat_cache is None or self._feat_cache[0] != key:
-            self._feat_cache = (key, ops.layernorm(ms_feat.contiguous(), self.feat_norm.weight, self.feat_norm.bias,
-                                                   self.feat_norm.eps))
-        return self._feat_cache[1]
+        n = self.feat_norm
+        extra = (n.weight.data_ptr(), n.weight._version, n.bias.data_ptr(), n.bias._version)
+        hit = None if torch.is_grad_enabled() else self._feat_cache.get(ms_feat, extra)
+        if hit is None:
+            hit = ops.layernorm(ms_feat.contiguous(), n.weight, n.bias, n.eps)
+            if not torch.is_grad_enabled():
+                self._feat_cache.put(ms_feat, hit, extra)
+        return hit
 
     def forward(self, sample, ms_feat, ms_feat_mask, spatial_shapes):
         """sample (B, C_q, H, W); ms_feat (B, N, sum(H_l*W_l), C_v); ms_feat_mask (B, N); returns the residual (B, C_q, H, W)."""
@@ -165,16 +169,18 @@ class MMFSNet(nn.Module):
                 blocks.append(block(ch, len(blocks) // 3, len(blocks)))                    # downsampler skip
         self.mmfs_down_blocks = nn.ModuleList(blocks)
         self.mmfs_mid_block = block(block_out_channels[-1], -1, len(blocks))
+        self._packed = SourceCache()       # the level-concatenated feature tensor, identity-checked (see _cache.py)
 
     def forward(self, sample: torch.Tensor, down_block_res_samples: List[torch.Tensor],
                 mmfs_features: List[torch.Tensor], mmfs_mask: torch.Tensor):
         assert len(down_block_res_samples) == len(self.mmfs_down_blocks)
         spatial_shapes = [(int(f.shape[-2]), int(f.shape[-1])) for f in mmfs_features]
-        key = tuple((f.data_ptr(), f._version, tuple(f.shape)) for f in mmfs_features)
-        if getattr(self, "_packed", None) is None or self._packed[0] != key:   # constant across denoise steps
+        # constant across the denoise steps of one loop: the same list of tensor objects comes back every step
+        feats = None if torch.is_grad_enabled() else self._packed.get(list(mmfs_features))
+        if feats is None:
             feats = torch.cat([f.flatten(3).transpose(2, 3) for f in mmfs_features], dim=2).contiguous()   # b n (h w) c
-            self._packed = (key, feats)
-        feats = self._packed[1]
+            if not torch.is_grad_enabled():
+                self._packed.put(list(mmfs_features), feats)
         new_res = ()
         for res, blk in zip(down_block_res_samples, self.mmfs_down_blocks):
             new_res += (res + blk(res, feats, mmfs_mask, spatial_shapes),)

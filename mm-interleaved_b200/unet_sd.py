@@ -336,15 +336,24 @@ class GraphedUNet:
 
 @torch.no_grad()
 def denoise_loop(unet, latents, cond, uncond, mmfs_features, mmfs_mask, mmfs_module, num_steps=50, guidance=7.5,
-                 num_train_timesteps=1000, cuda_graph: Optional[bool] = None):
+                 num_train_timesteps=1000, cuda_graph: Optional[bool] = None, scheduler=None, generator=None):
     """Classifier-free-guidance denoise loop in the shape of the patched pipeline ``__call__``
-    (utils/monkey_patch/sd_pipeline_monkey_patch.py:172-226: CFG duplicates the MMFS inputs, one UNet call on the
-    2B batch per step, ``uncond + g (text - uncond)``).  The scheduler arithmetic belongs to diffusers; a
-    deterministic DDIM (eta = 0) update on the SD 'scaled_linear' beta schedule stands in for it here.
-    ``cuda_graph=True`` captures the UNet evaluation once per loop and replays it per step (opt-in, see below)."""
-    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, num_train_timesteps, dtype=torch.float64) ** 2
-    acp = torch.cumprod(1.0 - betas, 0).float().to(latents.device)
-    ts = torch.linspace(num_train_timesteps - 1, 0, num_steps).round().long().to(latents.device)
+    (utils/monkey_patch/sd_pipeline_monkey_patch.py:153-218: ``set_timesteps``; CFG duplicates the MMFS inputs; per step
+    ``scale_model_input``, one UNet call on the 2B batch, ``uncond + g (text - uncond)``, ``scheduler.step``).
+    ``scheduler``: any object with ``set_timesteps / scale_model_input / step`` (scheduler.py; a diffusers scheduler
+    works too).  Default = the reference's choice, DDPM ancestral sampling on the SD-2.1-base schedule (sd.py:48-50),
+    its noise drawn from ``generator``.  ``cuda_graph=True`` captures the UNet evaluation once per loop and replays it
+    per step (opt-in, see below)."""
+    from .scheduler import DDPMScheduler, SD21_BASE_SCHEDULER
+    if scheduler is None:
+        scheduler = DDPMScheduler(**dict(SD21_BASE_SCHEDULER, num_train_timesteps=num_train_timesteps))
+    scheduler.set_timesteps(num_steps, device=latents.device)
+    ts_dev = scheduler.timesteps
+    ts_host = getattr(scheduler, "_host_timesteps", None)
+    if ts_host is None:
+        ts_host = [int(t) for t in ts_dev.tolist()]
+    own_step = hasattr(scheduler, "_host_timesteps")          # this repo's schedulers return the tensor directly
+    latents = latents * getattr(scheduler, "init_noise_sigma", 1.0)
     ctx = torch.cat([uncond, cond], 0)
     feats2 = [torch.cat([f, f], 0) for f in mmfs_features] if mmfs_features is not None else None
     mask2 = torch.cat([mmfs_mask, mmfs_mask], 0) if mmfs_mask is not None else None
@@ -354,8 +363,9 @@ def denoise_loop(unet, latents, cond, uncond, mmfs_features, mmfs_mask, mmfs_mod
         # captured graph serves many loops, which needs the per-loop MMFS feature caches refreshed in place.
         cuda_graph = False
     runner = None
-    for i, t in enumerate(ts):
-        x2 = torch.cat([latents, latents], 0)
+    for i, t_host in enumerate(ts_host):
+        t = ts_dev[i]
+        x2 = scheduler.scale_model_input(torch.cat([latents, latents], 0), t)
         if latents.is_cuda:
             x2 = x2.contiguous(memory_format=torch.channels_last)
         if cuda_graph:
@@ -365,9 +375,9 @@ def denoise_loop(unet, latents, cond, uncond, mmfs_features, mmfs_mask, mmfs_mod
         else:
             eps = unet(x2, t, ctx, mmfs_features=feats2, mmfs_mask=mask2, mmfs_module=mmfs_module)
         e_u, e_c = eps.chunk(2)
-        eps = (e_u + guidance * (e_c - e_u)).float()
-        a_t = acp[t]
-        a_prev = acp[ts[i + 1]] if i + 1 < len(ts) else torch.ones((), device=latents.device)
-        x0 = (latents.float() - (1 - a_t).sqrt() * eps) / a_t.sqrt()
-        latents = (a_prev.sqrt() * x0 + (1 - a_prev).sqrt() * eps).to(latents.dtype)
+        eps = e_u + guidance * (e_c - e_u)
+        if own_step:
+            latents = scheduler.step(eps, t_host, latents, generator=generator)
+        else:                                                  # diffusers-style object
+            latents = scheduler.step(eps, t, latents, generator=generator, return_dict=False)[0]
     return latents

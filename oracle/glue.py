@@ -103,3 +103,33 @@ def mmfs_features_for_image_decoder_ref(multiscale_features, text_ids, soi_token
                 dst[i, 0] = src[i - 1]
             mask[i, 0] = 1
     return feats, mask
+
+
+def text_head_ref(sd, hidden, orig_vocab, prefix="text_decoder."):
+    """TextDecoder.forward (decoders/decoder_text.py:152-157): ``head`` over the whole vocabulary, ``head_new`` added on
+    the columns of the new ids; both linears carry a bias (:43-46)."""
+    logits = hidden @ sd[prefix + "head.weight"].t() + sd[prefix + "head.bias"]
+    new = hidden @ sd[prefix + "head_new.weight"].t() + sd[prefix + "head_new.bias"]
+    logits[..., orig_vocab:] = logits[..., orig_vocab:] + new
+    return logits
+
+
+def gt_text_ids_ref(text_ids, attention_mask, st, ignore_prompt_token_offset=0):
+    """``_prepare_gt_text_ids`` (mm_interleaved.py:342-406) for the default branch (no ``gt_text_ids``, dataset not in
+    ``dataset_to_ignore_noimage_cond_loss``), written per element."""
+    B, L = text_ids.shape
+    gt = torch.full((B, L - 1), -100, dtype=text_ids.dtype)
+    for b in range(B):
+        off = ignore_prompt_token_offset if isinstance(ignore_prompt_token_offset, int) else ignore_prompt_token_offset[b]
+        for t in range(1, L):
+            tok, prev = int(text_ids[b, t]), int(text_ids[b, t - 1])
+            if t < off:                                                               # :352-359
+                continue
+            if tok in (st["pad_token_id"], st["image_token_id"], st["bos_token_id"]):  # :389-394, :402-404
+                continue
+            if int(attention_mask[b, t]) == 0:                                        # :395
+                continue
+            if prev == st["bos_token_id"] and tok == st["soi_token_id"]:              # :397-400
+                continue
+            gt[b, t - 1] = tok
+    return gt

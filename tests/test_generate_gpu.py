@@ -5,7 +5,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from oracle.glue import cross_attention_mask_ref, pack_mmfs_features_ref, prepare_mm_embeds_ref  # noqa: E402
+from oracle.glue import cross_attention_mask_ref, pack_mmfs_features_ref, prepare_mm_embeds_ref, text_head_ref  # noqa: E402
 from oracle.llama import llama_model_ref  # noqa: E402
 from tests.golden.make_golden import LLAMA_TINY, seeded_state_dict  # noqa: E402
 
@@ -20,6 +20,8 @@ def test_greedy_generation_matches_oracle_loop():
     sd = seeded_state_dict(model.state_dict(), seed=31337)
     sd["text_decoder.head.weight"][60:] = 0        # never emit the special ids: their logits stay 0 < max of 60 random logits
     sd["text_decoder.head_new.weight"].zero_()
+    sd["text_decoder.head.bias"][60:] = 0
+    sd["text_decoder.head_new.bias"].zero_()
     model.load_state_dict(sd)
     g = torch.Generator().manual_seed(3)
     L, n_tok = 20, 3
@@ -50,8 +52,7 @@ def test_greedy_generation_matches_oracle_loop():
         emb = prepare_mm_embeds_ref(emb, cur, vis["vis_embed"], sd["soi_token"], IMG, SOI)
         cross = torch.cat([cross0] + [cross0[:, -1:]] * step, dim=1)      # new tokens reuse the last mask row
         hid, _ = llama_model_ref(dec, emb, torch.ones_like(cur), None, feats, cross, ocfg)
-        logits = hid[:, -1] @ sd["text_decoder.head.weight"].t()
-        logits[:, 62:] += hid[:, -1] @ sd["text_decoder.head_new.weight"].t()
+        logits = text_head_ref(sd, hid[:, -1], 62)
         nxt = logits.argmax(-1)
         want.append(nxt)
         cur = torch.cat([cur, nxt[:, None]], dim=1)
@@ -74,6 +75,8 @@ def _setup(seed_weights=31337):
     sd = seeded_state_dict(model.state_dict(), seed=seed_weights)
     sd["text_decoder.head.weight"][60:] = 0
     sd["text_decoder.head_new.weight"].zero_()
+    sd["text_decoder.head.bias"][60:] = 0
+    sd["text_decoder.head_new.bias"].zero_()
     model.load_state_dict(sd)
     g = torch.Generator().manual_seed(3)
     L, n_tok = 20, 3
@@ -99,9 +102,7 @@ def _oracle_step_logits(cfg, sd, cur, ids, nimg, vis, step):
     emb = prepare_mm_embeds_ref(emb, cur, vis["vis_embed"], sd["soi_token"], 62, 63)
     cross = torch.cat([cross0] + [cross0[:, -1:]] * step, dim=1)
     hid, _ = llama_model_ref(dec, emb, torch.ones_like(cur), None, feats, cross, ocfg)
-    logits = hid[:, -1] @ sd["text_decoder.head.weight"].t()
-    logits[:, 62:] += hid[:, -1] @ sd["text_decoder.head_new.weight"].t()
-    return logits
+    return text_head_ref(sd, hid[:, -1], 62)
 
 
 def test_min_length_eos_list_and_repetition_penalty_follow_hf_semantics():

@@ -127,6 +127,9 @@ def test_graphed_denoise_loop_matches_eager():
     cond = torch.randn((2, 7, 128), device=DEV, dtype=torch.bfloat16, generator=g)
     feats = [torch.randn((2, 1, 128, s, s), device=DEV, dtype=torch.bfloat16, generator=g) for s in (32, 16, 8, 4)]
     mask = torch.ones((2, 1), device=DEV)
-    a = unet_sd.denoise_loop(unet, lat, cond, torch.zeros_like(cond), feats, mask, net, num_steps=4, cuda_graph=False)
-    b = unet_sd.denoise_loop(unet, lat, cond, torch.zeros_like(cond), feats, mask, net, num_steps=4, cuda_graph=True)
+    from mm_interleaved_b200.scheduler import DDIMScheduler      # deterministic update: the two runs must agree
+    a = unet_sd.denoise_loop(unet, lat, cond, torch.zeros_like(cond), feats, mask, net, num_steps=4, cuda_graph=False,
+                             scheduler=DDIMScheduler())
+    b = unet_sd.denoise_loop(unet, lat, cond, torch.zeros_like(cond), feats, mask, net, num_steps=4, cuda_graph=True,
+                             scheduler=DDIMScheduler())
     assert torch.isfinite(a.float()).all() and (a.float() - b.float()).abs().max() <= 1e-2 * a.float().abs().max()
