@@ -133,3 +133,70 @@ def load():
 def torch_nn():
     import torch.nn as nn
     return nn
+
+
+class AttrDict(dict):
+    """dict with attribute access (what the reference's OmegaConf configs look like to its constructors)."""
+    __getattr__ = dict.__getitem__
+
+
+def _xformers_stub():
+    """xformers 0.0.20 is not in this image.  The reference calls exactly one function of it on the encoder path,
+    ``xformers.ops.memory_efficient_attention(q, k, v, attn_bias)`` with (B, T, H, hd) operands (xattn.py:70-72), whose
+    published semantics are softmax(q k^T / sqrt(hd) + bias) v -- also spelled out in the reference's own commented
+    eager code (xattn.py:75-135).  That formula is what the stub computes."""
+    import torch
+    xf, xo = types.ModuleType("xformers"), types.ModuleType("xformers.ops")
+
+    class LowerTriangularMask:  # noqa: D401 - marker type only
+        pass
+
+    def memory_efficient_attention(q, k, v, attn_bias=None, p=0.0, scale=None):
+        s = torch.einsum("bqhd,bkhd->bhqk", q, k) * (q.shape[-1] ** -0.5 if scale is None else scale)
+        if attn_bias is not None:
+            T, S = q.shape[1], k.shape[1]
+            s = s.masked_fill(~torch.tril(torch.ones(T, S, dtype=torch.bool)), float("-inf"))
+        return torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, -1), v)
+
+    xo.memory_efficient_attention, xo.LowerTriangularMask, xf.ops = memory_efficient_attention, LowerTriangularMask, xo
+    return xf, xo
+
+
+def load_visual():
+    """The reference's visual tokenizer stack, importable here with three shims (none touches /root/reference):
+    (1) the docstring decorators / constants ``vit_adapter_hf.py`` imports from transformers 4.31 that 5.x dropped are
+    supplied as no-ops; (2) ``xformers`` is the stub above; (3) ``timm.DropPath`` is Identity (never active).  The CLIP
+    encoder layers and the Q-Former glue then come from the transformers version in this image (5.x) as a stand-in
+    for the pinned 4.31; the attention classes (``CLIPXAttention``, the qk-norm ``Blip2QFormerMultiHeadAttention``), the
+    adapter, ``PerceiverResampler`` and ``VisualTokenizer`` are the reference's own files.  Returns a namespace."""
+    ns = load()                                    # registers the package stubs + adapter_modules (timm stub)
+    import transformers.models.clip.modeling_clip as mc
+    import transformers.utils as tu
+    for name in ("CLIP_VISION_INPUTS_DOCSTRING", "CLIP_START_DOCSTRING"):
+        if not hasattr(mc, name):
+            setattr(mc, name, "")
+
+    def _passthrough(*a, **k):
+        return lambda fn: fn
+
+    for name in ("add_start_docstrings", "add_start_docstrings_to_model_forward", "replace_return_docstrings"):
+        if not hasattr(tu, name):
+            setattr(tu, name, _passthrough)
+    if "xformers" not in sys.modules:
+        xf, xo = _xformers_stub()
+        sys.modules["xformers"], sys.modules["xformers.ops"] = xf, xo
+    root = os.path.join(REF_ROOT, _PKG, "models")
+    va = os.path.join(root, "encoders", "vit_adapter")
+    pk = f"{_PKG}.models.encoders.vit_adapter"
+    mp = os.path.join(root, "utils", "monkey_patch")
+    _stub(f"{_PKG}.models.utils.monkey_patch", mp)
+    qk = _load(f"{_PKG}.models.utils.monkey_patch.blip2_qknorm_monkey_patch", os.path.join(mp, "blip2_qknorm_monkey_patch.py"))
+    qk.replace_blip2_attn_with_qknorm_attn()       # inference.py:19
+    ns.qknorm = qk
+    ns.xattn = _load(pk + ".xattn", os.path.join(va, "xattn.py"))
+    ns.clip_vit = _load(pk + ".clip_vit_hf", os.path.join(va, "clip_vit_hf.py"))
+    ns.vit_adapter = _load(pk + ".vit_adapter_hf", os.path.join(va, "vit_adapter_hf.py"))
+    sys.modules[pk].clip_vit_adapter_hf = ns.vit_adapter.clip_vit_adapter_hf
+    ns.perceiver = _load(f"{_PKG}.models.decoders.perceiver", os.path.join(root, "decoders", "perceiver.py"))
+    ns.visual_tokenizer = _load(f"{_PKG}.models.encoders.visual_tokenizer", os.path.join(root, "encoders", "visual_tokenizer.py"))
+    return ns

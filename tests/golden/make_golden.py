@@ -394,9 +394,98 @@ def make_imgdec():
     print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+# ---------------------------------------------------------------------------------------------------------
+# visual tokenizer: the reference's OWN VisualTokenizer / CLIPVisionTransformerAdapter / CLIPXAttention / qk-norm
+# Q-Former attention / PerceiverResampler files (encoders/visual_tokenizer.py:11-101, vit_adapter/vit_adapter_hf.py:36-167,
+# vit_adapter/xattn.py:20-141, utils/monkey_patch/blip2_qknorm_monkey_patch.py:8-152, decoders/perceiver.py) executed
+# here through oracle/ref_loader.load_visual() -- see its docstring for the three shims (transformers 5.x CLIP / Q-Former
+# glue standing in for 4.31, the xformers attention formula, timm.DropPath = Identity).
+# ---------------------------------------------------------------------------------------------------------
+TOKENIZER_TINY = dict(clip=dict(hidden_size=64, intermediate_size=128, num_hidden_layers=24, num_attention_heads=4,
+                                image_size=56, patch_size=14),
+                      perceiver=dict(num_queries=5, hidden_size=48, encoder_hidden_size=64, cross_attention_frequency=2,
+                                     num_hidden_layers=2, num_attention_heads=4, intermediate_size=96, qk_normalization=True),
+                      llm_hidden_size=80, grid_size=4)
+QFORMER_TINY = dict(num_queries=8, hidden_size=192, encoder_hidden_size=256, num_hidden_layers=4, num_attention_heads=3,
+                    cross_attention_frequency=2, intermediate_size=384, qk_normalization=True)
+
+
+def tokenizer_state_dict(template, seed=909):
+    sd = adapter_state_dict(template, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    for k in list(sd):
+        if k.endswith("position_ids") or k == "pos_embed":
+            sd[k] = template[k].clone()                                  # index buffer / frozen sin-cos table
+        elif k.endswith("q_norm.weight") or k.endswith("k_norm.weight") or "layer_norm" in k and k.endswith("weight") \
+                or k.endswith("LayerNorm.weight") or k.endswith("_ln.weight") or k.endswith("layrnorm.weight"):
+            sd[k] = 1.0 + 0.1 * torch.randn(template[k].shape, generator=g)
+        elif k.endswith("proj.weight") and k.count(".") == 1:
+            sd[k] = 0.05 * torch.randn(template[k].shape, generator=g)   # 1e-3 init in the reference: make it count
+    return sd
+
+
+def tokenizer_inputs(seed=41):
+    return torch.rand((2, 3, 56, 56), generator=torch.Generator().manual_seed(seed))
+
+
+def qformer_inputs(seed=43):
+    g = torch.Generator().manual_seed(seed)
+    enc = torch.randn((2, 17, QFORMER_TINY["encoder_hidden_size"]), generator=g)
+    mask = torch.ones((2, 17), dtype=torch.long)
+    mask[1, 10:] = 0
+    return enc, mask
+
+
+def make_tokenizer():
+    from transformers import CLIPVisionConfig
+    ns = ref_loader.load_visual()
+    c = TOKENIZER_TINY
+    cfg = CLIPVisionConfig(**c["clip"], hidden_act="quick_gelu", layer_norm_eps=1e-5)
+    cfg._attn_implementation = "eager"
+
+    def tiny_encoder(model_path=None, **kw):        # clip_vit_adapter_hf (vit_adapter_hf.py:236-258) minus from_pretrained
+        m = ns.vit_adapter.CLIPVisionAdapterModel(cfg)
+        ns.xattn.convert_clip_visual_attn(m)
+        m.vision_model.set_vis_embed_requires_grad(False)
+        return m
+
+    ns.visual_tokenizer.clip_vit_adapter_hf = tiny_encoder
+    pc = ref_loader.AttrDict(c["perceiver"], gradient_checkpointing=False, hidden_dropout_prob=0.0,
+                             attention_probs_dropout_prob=0.0)
+    tok = ns.visual_tokenizer.VisualTokenizer(encoder_model_path="", perceiver_config=pc, llm_hidden_size=c["llm_hidden_size"],
+                                              grid_size=c["grid_size"]).eval()
+    sd = tokenizer_state_dict(tok.state_dict())
+    tok.load_state_dict(sd)
+    with torch.no_grad():
+        out = tok(tokenizer_inputs())
+    path = os.path.join(HERE, "tokenizer_tiny.npz")
+    np.savez_compressed(path, vis_embed=out["vis_embed"].numpy(), image_embeds=out["image_embeds"].numpy(),
+                        **{f"ms{i}": f.numpy() for i, f in enumerate(out["multiscale_features"])},
+                        keys=np.array(sorted(sd.keys())),
+                        checksum=np.array(float(sum(v.double().sum() for v in sd.values()))))
+    print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+    # the Q-Former alone with a key-padding mask (the image decoder's use, decoder_image.py:132-136)
+    q = dict(QFORMER_TINY)
+    per = ns.perceiver.PerceiverResampler(**q, gradient_checkpointing=False, hidden_dropout_prob=0.0,
+                                          attention_probs_dropout_prob=0.0).eval()
+    sdq = tokenizer_state_dict(per.state_dict(), seed=919)
+    per.load_state_dict(sdq)
+    enc, mask = qformer_inputs()
+    with torch.no_grad():
+        o_mask = per(encoder_hidden_states=enc, encoder_attention_mask=mask, return_dict=False)[0]
+        o_nomask = per(encoder_hidden_states=enc, encoder_attention_mask=None, return_dict=False)[0]
+    path = os.path.join(HERE, "qformer_qknorm_tiny.npz")
+    np.savez_compressed(path, out_masked=o_mask.numpy(), out_unmasked=o_nomask.numpy(), keys=np.array(sorted(sdq.keys())),
+                        checksum=np.array(float(sum(v.double().sum() for v in sdq.values()))))
+    print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["msda", "mmfs", "llama", "mmfsnet", "adapter", "imgdec"]
+    which = sys.argv[1:] or ["msda", "mmfs", "llama", "mmfsnet", "adapter", "imgdec", "tokenizer"]
+    if "tokenizer" in which:
+        make_tokenizer()
     if "imgdec" in which:
         make_imgdec()
     if "adapter" in which:
