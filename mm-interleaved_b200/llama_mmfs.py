@@ -124,12 +124,31 @@ class StaticKV:
     positions.  Passing it as ``past_key_value`` makes the layer append IN PLACE instead of the reference's
     ``torch.cat`` (modeling_llama_mmfs.py:236-239), which re-copies the whole cache of every layer for every token."""
 
-    __slots__ = ("k", "v", "length")
+    __slots__ = ("k", "v", "length", "slot")
 
     def __init__(self, batch, max_len, heads, head_dim, dtype, device):
         self.k = torch.empty((batch, max_len, heads, head_dim), dtype=dtype, device=device)
         self.v = torch.empty_like(self.k)
         self.length = 0
+        # CUDA-graph decode (mm_interleaved.py::_GraphedGreedyDecoder): a (1,) int64 DEVICE tensor holding the slot the
+        # next token is written to.  While set, a step appends at ``slot`` (index_copy_, no host integer involved),
+        # attends over the WHOLE buffer under the caller's key mask, and ``length`` stays pinned at max_len - 1.
+        self.slot = None
+
+
+class PreparedVision:
+    """Image-side state of the MMFS cross-attention layers for ONE batch of images: per layer, ``value`` =
+    value_proj(RMSNorm(vision)) (modeling_llama_mmfs.py:353, mmfs.py:165-172) -- everything those layers derive from
+    the images alone.  ``LlamaModel.prepare_vision`` fills it once; passing it as ``vision_hidden_states`` to prefill
+    and to every decode step replaces the per-layer, per-token recomputation of the reference (and the implicit
+    tensor-identity caches) by explicit scoping: the object lives exactly as long as its generate / forward call.
+    With ``out=`` the values are written into existing storage (the static buffers a decode graph reads)."""
+
+    __slots__ = ("raw_shape", "values")
+
+    def __init__(self, raw_shape):
+        self.raw_shape = tuple(raw_shape)        # (B, n_img, hw, C) of the packed feature tensor
+        self.values = {}                          # layer index -> (B, n_img*hw, M, D)
 
 
 class LlamaAttention(nn.Module):
@@ -173,7 +192,15 @@ class LlamaAttention(nn.Module):
             position_ids = torch.arange(past, past + T, device=hidden_states.device)
         cos, sin = self.rope_tables(hidden_states.device, past + T)
         ops.rope_qk_(q, k, cos, sin, position_ids)
-        if static:
+        if static and past_key_value.slot is not None:          # graph decode: device-side slot, whole buffer visible
+            if T != 1:
+                raise RuntimeError("StaticKV.slot (graph decode) takes one token per step")
+            past_key_value.k.index_copy_(1, past_key_value.slot, k)
+            past_key_value.v.index_copy_(1, past_key_value.slot, v)
+            k, v = past_key_value.k, past_key_value.v
+            past = k.shape[1] - 1
+            present = past_key_value
+        elif static:
             if past + T > past_key_value.k.shape[1]:
                 raise RuntimeError(f"StaticKV of {past_key_value.k.shape[1]} positions cannot take {past} + {T}")
             past_key_value.k[:, past:past + T].copy_(k)
@@ -240,29 +267,40 @@ class LlamaMMFSAttention(nn.Module):
             self._gated = (key, (w.detach().float() * t).to(w.dtype), (b.detach().float() * t).to(b.dtype))
         return self._gated[1], self._gated[2]
 
+    def project_vision(self, vision_hidden_states):
+        """value_proj(RMSNorm(vision)) as (B, n_img*hw, M, D): the image-only part of this layer (:353, mmfs.py:165-172)."""
+        return self.attn.project_value(self.norm2(vision_hidden_states))
+
     def forward(self, hidden_states, vision_hidden_states=None, cross_attention_mask=None, residual=None, inplace=False):
         h = self.norm1(hidden_states)
-        # RMSNorm(vision) depends only on the images: reuse it while the SAME tensor object is passed again (the decode
-        # steps of one generate call); modeling_llama_mmfs.py:353 recomputes it per layer per token
-        w2 = self.norm2.weight
-        vextra = (w2.data_ptr(), w2._version)
-        v = None if torch.is_grad_enabled() else self._vision_cache.get(vision_hidden_states, vextra)
-        if v is None:
-            v = self.norm2(vision_hidden_states)
-            if not torch.is_grad_enabled():
-                self._vision_cache.put(vision_hidden_states, v, vextra)
-        _, n_img, hw, _ = v.shape
+        value = None
+        if isinstance(vision_hidden_states, PreparedVision):
+            value = vision_hidden_states.values[self.layer_idx]
+            _, n_img, hw, _ = vision_hidden_states.raw_shape
+            v = None
+        else:
+            # RMSNorm(vision) depends only on the images: reuse it while the SAME tensor object is passed again (the
+            # decode steps of one generate call); modeling_llama_mmfs.py:353 recomputes it per layer per token
+            w2 = self.norm2.weight
+            vextra = (w2.data_ptr(), w2._version)
+            v = None if torch.is_grad_enabled() else self._vision_cache.get(vision_hidden_states, vextra)
+            if v is None:
+                v = self.norm2(vision_hidden_states)
+                if not torch.is_grad_enabled():
+                    self._vision_cache.put(vision_hidden_states, v, vextra)
+            _, n_img, hw, _ = v.shape
         shapes, starts, ref = self._geometry(h.device, n_img, hw, h.shape[1])
         if not torch.is_grad_enabled():
             gw, gb = self._gated_output()
             out = self.attn(query=h, reference_points=ref, input_flatten=v, input_spatial_shapes=shapes,
                             input_level_start_index=starts, input_padding_mask=None, attention_mask=cross_attention_mask,
-                            output_weight=gw, output_bias=gb)
+                            output_weight=gw, output_bias=gb, value=value)
             if residual is None:
                 return out
             return residual.add_(out) if inplace else residual + out
         out = self.attn(query=h, reference_points=ref, input_flatten=v, input_spatial_shapes=shapes,
-                        input_level_start_index=starts, input_padding_mask=None, attention_mask=cross_attention_mask)
+                        input_level_start_index=starts, input_padding_mask=None, attention_mask=cross_attention_mask,
+                        value=value)
         gate = self.gate.tanh().to(out.dtype)
         if residual is None:
             return out * gate
@@ -324,6 +362,22 @@ class LlamaModel(nn.Module):
         H = self.config.num_attention_heads
         return [StaticKV(batch, max_len, H, self.config.hidden_size // H, dtype or p.dtype, device or p.device)
                 for _ in self.layers]
+
+    @torch.no_grad()
+    def prepare_vision(self, vision_hidden_states, out: Optional[PreparedVision] = None) -> PreparedVision:
+        """Run the image-only part of every cross-attention layer once (see ``PreparedVision``)."""
+        pv = PreparedVision(vision_hidden_states.shape) if out is None else out
+        if tuple(vision_hidden_states.shape) != pv.raw_shape:
+            raise RuntimeError(f"prepare_vision: features {tuple(vision_hidden_states.shape)} do not fit {pv.raw_shape}")
+        for layer in self.layers:
+            if layer.llama_cross_attn is None:
+                continue
+            val = layer.llama_cross_attn.project_vision(vision_hidden_states)
+            if out is None:
+                pv.values[layer.layer_idx] = val
+            else:
+                pv.values[layer.layer_idx].copy_(val)
+        return pv
 
     def get_input_embeddings(self):
         return self.embed_tokens

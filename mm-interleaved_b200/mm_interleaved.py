@@ -296,6 +296,119 @@ class ImageDecoder(nn.Module):
         return out
 
 
+class _GraphedGreedyDecoder:
+    """Static state + one CUDA graph of a greedy decode step for ``InterleavedForward`` (see ``enable_decode_graphs``).
+
+    Everything that changes from token to token lives in DEVICE tensors the graph updates itself -- the slot the new
+    key/value row goes to, the key mask over the whole static cache, the position ids, the step counter, the finished
+    flags, the output ids -- so generating N tokens is N ``graph.replay()`` calls with no host synchronisation.  The
+    image-side tensors of the cross-attention layers are a ``PreparedVision`` over static storage, refilled eagerly once
+    per call (a graph replay bypasses Python, so nothing inside the graph may depend on a tensor-identity cache)."""
+
+    def __init__(self, owner, B, t_max, feats_shape, dtype, device, eos_ids, pad_id, min_length, max_new):
+        from .llama_mmfs import PreparedVision
+        self.owner, self.B, self.t_max, self.max_new, self.min_length = owner, B, t_max, max_new, int(min_length)
+        model = owner.mm_decoder
+        n_img = feats_shape[1]
+        self.past = model.static_cache(B, t_max, dtype=dtype, device=device)
+        self.pv = PreparedVision(feats_shape)
+        probe = model.prepare_vision(torch.zeros(feats_shape, dtype=dtype, device=device))
+        for idx, val in probe.values.items():
+            self.pv.values[idx] = torch.empty_like(val)
+        V = owner.text_decoder.head.weight.shape[0]
+        self.logits = torch.zeros((B, V), dtype=torch.float32, device=device)
+        self.key_mask = torch.zeros((B, t_max), dtype=torch.uint8, device=device)
+        self.pos = torch.zeros((B, 1), dtype=torch.long, device=device)
+        self.cur = torch.zeros((1,), dtype=torch.long, device=device)
+        self.step = torch.zeros((1,), dtype=torch.long, device=device)
+        self.finished = torch.zeros((B,), dtype=torch.bool, device=device)
+        self.out_ids = torch.zeros((B, max_new), dtype=torch.long, device=device)
+        self.cross_last = torch.zeros((B, 1, n_img), dtype=torch.float32, device=device)
+        self.eos = torch.tensor(eos_ids, dtype=torch.long, device=device) if eos_ids else None
+        self.pad = torch.tensor(int(pad_id), dtype=torch.long, device=device)
+        self.neg_inf = torch.tensor(float("-inf"), dtype=torch.float32, device=device)
+        self.zero = torch.zeros((), dtype=torch.float32, device=device)
+        self.graph = None
+        self.launches = 0
+
+    def _set_graph_mode(self, on: bool, length: int = 0):
+        for c in self.past:
+            c.slot = self.cur if on else None
+            c.length = self.t_max - 1 if on else length
+
+    def _step(self):
+        """One token: processors + arg-max on the pending logits, bookkeeping, decoder forward on the chosen token."""
+        o = self.owner
+        scores = self.logits
+        if self.eos is not None and self.min_length > 0:                   # HF MinLengthLogitsProcessor
+            bias = torch.where(self.step < self.min_length, self.neg_inf, self.zero)
+            scores = scores.index_add(1, self.eos, bias.expand(self.B, self.eos.numel()).contiguous())
+        nxt = scores.argmax(-1)
+        if self.eos is not None:
+            nxt = torch.where(self.finished, self.pad, nxt)
+            self.finished.logical_or_((nxt[:, None] == self.eos[None, :]).any(dim=1))
+        self.out_ids.index_copy_(1, self.step, nxt[:, None])
+        self.key_mask.index_fill_(1, self.cur, 1)                          # the fed token's cache slot becomes visible
+        self.pos.add_(1)
+        hid = o.mm_decoder(inputs_embeds=o.mm_decoder.embed_tokens(nxt[:, None]), attention_mask=self.key_mask,
+                           position_ids=self.pos, past_key_values=self.past, vision_hidden_states=self.pv,
+                           cross_attention_mask=self.cross_last, use_cache=True, return_dict=True).last_hidden_state
+        self.logits.copy_(o.text_decoder.logits(hid)[:, -1].float())
+        self.step.add_(1)
+        self.cur.add_(1)
+
+    def _reset(self, L, attention_mask, position_ids, cross, logits0):
+        self.key_mask.zero_()
+        self.key_mask[:, :L].copy_(attention_mask.to(torch.uint8))
+        self.pos.copy_(position_ids[:, -1:])
+        self.cur.fill_(L)
+        self.step.zero_()
+        self.finished.zero_()
+        self.out_ids.fill_(int(self.pad))
+        self.cross_last.copy_(cross[:, -1:, :])
+        self.logits.copy_(logits0)
+
+    def generate(self, mm_embeds, cross, feats, attention_mask, position_ids):
+        from . import ops
+        o = self.owner
+        B, L, _ = mm_embeds.shape
+        if L + self.max_new > self.t_max:
+            raise RuntimeError("prompt + new tokens exceed the captured cache length")
+        o.mm_decoder.prepare_vision(feats, out=self.pv)                     # eager, into the static buffers the graph reads
+        self._set_graph_mode(False, 0)
+        out = o.mm_decoder(inputs_embeds=mm_embeds, attention_mask=attention_mask, position_ids=position_ids,
+                           past_key_values=self.past, vision_hidden_states=self.pv, cross_attention_mask=cross,
+                           use_cache=True, return_dict=True)               # prefill straight into the static cache
+        logits0 = o.text_decoder.logits(out.last_hidden_state[:, -1:])[:, -1].float()
+        for c in self.past:                                                 # masked slots must hold finite numbers
+            c.k[:, L:].zero_()
+            c.v[:, L:].zero_()
+        self._set_graph_mode(True)
+        if self.graph is None:
+            self._reset(L, attention_mask, position_ids, cross, logits0)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                                          # lazy handles, weight-derived caches, RoPE tables
+                    self._step()
+            torch.cuda.current_stream().wait_stream(side)
+            self._reset(L, attention_mask, position_ids, cross, logits0)
+            before = ops.launch_counter[0]
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._step()
+            self.launches = ops.launch_counter[0] - before
+            for c in self.past:                                             # the warm-up steps wrote slots L, L+1
+                c.k[:, L:].zero_()
+                c.v[:, L:].zero_()
+        self._reset(L, attention_mask, position_ids, cross, logits0)
+        for _ in range(self.max_new):
+            self.graph.replay()
+        ops.launch_counter[0] += self.launches * self.max_new
+        self._set_graph_mode(False, L)
+        return self.out_ids.clone()
+
+
 class InterleavedForward(nn.Module):
     """``mm_decoder`` + ``text_decoder`` + ``soi_token`` of ``MMInterleaved`` with the forward path of
     ``MMInterleaved.forward`` up to the text logits.  Image embeddings / multi-scale maps come from the visual
@@ -313,6 +426,29 @@ class InterleavedForward(nn.Module):
         self.context_feat_proj = nn.Linear(config.hidden_size, config.hidden_size)       # mm_interleaved.py:99
         self.seq_len = seq_len
         self.image_decoder = image_decoder                                                # ImageDecoder or None
+        self._decode_graphs = None                                                        # enable_decode_graphs()
+
+    def enable_decode_graphs(self, enabled: bool = True) -> "InterleavedForward":
+        """Greedy ``generate_texts`` then replays ONE captured CUDA graph per generated token (embedding -> 40 layers ->
+        head -> logits processors -> arg-max -> state update, ~1000 kernels) instead of launching them from Python; the
+        graph, its static KV cache and input buffers are kept per (batch, cache length, image count) and reused by
+        later calls (causal_lm_cascade.py:171-204 is the loop it replaces)."""
+        self._decode_graphs = {} if enabled else None
+        return self
+
+    @torch.no_grad()
+    def _graphed_greedy(self, mm_embeds, cross, feats, attention_mask, position_ids, max_new_tokens, eos_ids, pad_id, min_length):
+        B, L, _ = mm_embeds.shape
+        t_max = ((L + max_new_tokens + 255) // 256) * 256                  # cache-length bucket: one graph serves nearby prompts
+        key = (B, t_max, tuple(feats.shape), mm_embeds.dtype, mm_embeds.device, tuple(eos_ids), int(pad_id), int(min_length),
+               int(max_new_tokens))
+        dec = self._decode_graphs.get(key)
+        if dec is None:
+            if len(self._decode_graphs) >= 4:
+                self._decode_graphs.pop(next(iter(self._decode_graphs)))
+            dec = self._decode_graphs[key] = _GraphedGreedyDecoder(self, B, t_max, feats.shape, mm_embeds.dtype, mm_embeds.device,
+                                                                   eos_ids, pad_id, min_length, max_new_tokens)
+        return dec.generate(mm_embeds, cross, feats, attention_mask, position_ids)
 
     def prepare(self, text_ids, visual_output, num_image_per_seq, max_num_image: int):
         st = self.special_token_dict
@@ -386,6 +522,13 @@ class InterleavedForward(nn.Module):
         eos_ids = [] if eos_token_id is None else ([int(eos_token_id)] if isinstance(eos_token_id, int) else [int(e) for e in eos_token_id])
         mm_embeds, cross, feats = self.prepare(text_ids, visual_output, num_image_per_seq, max_num_image)
         position_ids = (attention_mask.long().cumsum(-1) - 1).masked_fill(attention_mask == 0, 1)   # causal_lm_cascade.py:181-183
+        graphed = (self._decode_graphs is not None and static_cache and not use_nucleus_sampling and
+                   repetition_penalty == 1.0 and text_ids.is_cuda and max_new_tokens > 0)
+        if graphed:
+            return self._graphed_greedy(mm_embeds, cross, feats, attention_mask, position_ids, max_new_tokens, eos_ids,
+                                        pad_token_id, min_length)
+        # the image-only half of the 10 cross-attention layers, once per call (PreparedVision)
+        feats = self.mm_decoder.prepare_vision(feats)
         # pre-allocated per-layer caches appended in place (the reference's cat-per-token re-copies every layer's cache)
         past = self.mm_decoder.static_cache(B, L + max_new_tokens, dtype=mm_embeds.dtype, device=mm_embeds.device) if static_cache else None
         out = self.mm_decoder(inputs_embeds=mm_embeds, attention_mask=attention_mask, position_ids=position_ids,

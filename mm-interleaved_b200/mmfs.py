@@ -144,13 +144,15 @@ class MMFS(nn.Module):
         return value
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
-                input_padding_mask=None, attention_mask=None, output_weight=None, output_bias=None):
+                input_padding_mask=None, attention_mask=None, output_weight=None, output_bias=None, value=None):
         """Reference signature (mmfs.py:120-129).  ``output_weight`` / ``output_bias`` (extension) replace
-        ``output_proj`` for callers that fold a following linear map into it (MMFSBlock's 1x1 conv)."""
+        ``output_proj`` for callers that fold a following linear map into it (MMFSBlock's 1x1 conv); ``value``
+        (extension) supplies value_proj(input_flatten) computed by the caller (``input_flatten`` may then be None)."""
         N, Len_q, _ = query.shape
-        _, n_images, hw, _ = input_flatten.shape
         assert attention_mask is not None and attention_mask.ndim in (2, 3)
-        assert attention_mask.shape[-1] == n_images
+        n_images = attention_mask.shape[-1]
+        if input_flatten is not None:
+            assert input_flatten.shape[1] == n_images
         if input_spatial_shapes.shape[0] != n_images * self.n_levels:
             raise RuntimeError("input_spatial_shapes must list n_images * n_levels levels")
         if n_images >= self.max_num_image_per_seq:
@@ -164,7 +166,8 @@ class MMFS(nn.Module):
         if not query.is_cuda:
             raise RuntimeError("MMFS (B200) runs on CUDA tensors only (no CPU fallback)")
 
-        value = self.project_value(input_flatten, input_padding_mask)
+        if value is None:
+            value = self.project_value(input_flatten, input_padding_mask)
         relpos = relative_image_index(attention_mask, Len_q)
         w_cat, b_cat, rtable = self._fused_weights()
         q1 = self.dynamic_offset_mask(query)                       # once per token

@@ -231,3 +231,28 @@ def test_beam_search_matches_the_hf_algorithm_on_the_oracle_decoder():
         if len(x) < width:
             want[i, len(x)] = eos[0]
     assert torch.equal(got, want), (got, want)
+
+
+def test_graphed_greedy_decode_matches_eager_across_calls_with_new_images():
+    """``enable_decode_graphs()``: one CUDA graph per generated token, static KV cache / masks / PreparedVision buffers
+    reused by later calls.  Tokens must equal the eager loop's (which equals the oracle loop, first test) -- also on the
+    SECOND call with different images and a different prompt mask, which replays the graph captured by the first."""
+    cfg, dev, sd, ids, nimg, vis, vis_d = _setup()
+    g = torch.Generator().manual_seed(123)
+    vis2_d = {"vis_embed": (torch.randn(vis["vis_embed"].shape, generator=g) * 0.5).cuda(),
+              "multiscale_features": [(torch.randn(f.shape, generator=g) * 2).cuda() for f in vis["multiscale_features"]]}
+    mask2 = torch.ones_like(ids)
+    mask2[1, :2] = 0                                                   # left padding on the second sequence
+    kw = dict(max_new_tokens=7, eos_token_id=[2, 17], min_length=3)
+    eager_a = dev.generate_texts(ids.cuda(), vis_d, nimg.cuda(), 2, **kw).cpu()
+    eager_b = dev.generate_texts(ids.cuda(), vis2_d, nimg.cuda(), 2, attention_mask=mask2.cuda(), **kw).cpu()
+    assert not torch.equal(eager_a, eager_b)
+    dev.enable_decode_graphs()
+    graph_a = dev.generate_texts(ids.cuda(), vis_d, nimg.cuda(), 2, **kw).cpu()
+    graph_b = dev.generate_texts(ids.cuda(), vis2_d, nimg.cuda(), 2, attention_mask=mask2.cuda(), **kw).cpu()
+    graph_a2 = dev.generate_texts(ids.cuda(), vis_d, nimg.cuda(), 2, **kw).cpu()
+    assert len(dev._decode_graphs) == 1                                # one captured graph served all three calls
+    assert torch.equal(graph_a, eager_a), (graph_a, eager_a)
+    assert torch.equal(graph_b, eager_b), (graph_b, eager_b)
+    assert torch.equal(graph_a2, eager_a)
+    dev.enable_decode_graphs(False)
