@@ -77,7 +77,7 @@ def transformer_block_ref(sd, p, x, ctx, heads):
     return x + _lin(sd, p + ".ff.net.2", h * F.gelu(gate))
 
 
-def transformer2d_ref(sd, p, x, ctx, head_dim=64, groups=32):
+def transformer2d_ref(sd, p, x, ctx, heads=None, groups=32, head_dim=64):
     """``Transformer2DModel.forward`` with ``use_linear_projection`` (SD 2.x; transformer_2d.py): GN(eps 1e-6) ->
     (B, HW, C) -> proj_in -> blocks -> proj_out -> (B, C, H, W) + residual."""
     B, C, H, W = x.shape
@@ -88,18 +88,22 @@ def transformer2d_ref(sd, p, x, ctx, head_dim=64, groups=32):
     h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)
     h = _lin(sd, p + ".proj_in", h)
     for i in range(_count(sd, p + ".", "transformer_blocks")):
-        h = transformer_block_ref(sd, f"{p}.transformer_blocks.{i}", h, ctx, inner // head_dim)
+        h = transformer_block_ref(sd, f"{p}.transformer_blocks.{i}", h, ctx, heads if heads else inner // head_dim)
     h = _lin(sd, p + ".proj_out", h)
     return h.reshape(B, H, W, C).permute(0, 3, 1, 2) + x
 
 
 def unet_forward_ref(sd, sample, timestep, encoder_hidden_states, mmfs_features=None, mmfs_mask=None, mmfs_module=None,
-                     head_dim=64):
+                     attention_head_dim=(5, 10, 20, 20)):
     """Patched forward, sd_unet_forward_monkey_patch.py: time embedding :103-128, conv_in :236, down blocks :253-283
     (``down_block_res_samples`` collects conv_in's output and every resnet(+attention) / downsampler output), mid block
     :301-311, the MMFS hook :316-326 (``mmfs_module(sample, down_block_res_samples, mmfs_features, mmfs_mask)`` -- any
     callable with that signature, e.g. the MMFSNet oracle), up blocks :329-362 (each pops ``len(resnets)`` skips),
-    conv_norm_out -> SiLU -> conv_out :365-368.  fp32 CPU tensors."""
+    conv_norm_out -> SiLU -> conv_out :365-368.  fp32 CPU tensors.  ``attention_head_dim`` is the UNet config entry of
+    that name, which diffusers 0.20 uses as the NUMBER of heads per down block (unet_2d_condition.py: ``num_attention_heads
+    = num_attention_heads or attention_head_dim``; SD-2.1: 5/10/20/20 heads of 64); the mid block takes the last entry,
+    the up blocks the reversed list."""
+    heads = list(attention_head_dim)
     sd = {k: v.float() for k, v in sd.items()}
     t = torch.as_tensor(timestep).reshape(-1).expand(sample.shape[0])
     temb_dim = sd["time_embedding.linear_1.weight"].shape[1]
@@ -113,7 +117,7 @@ def unet_forward_ref(sd, sample, timestep, encoder_hidden_states, mmfs_features=
         for i in range(_count(sd, p + ".", "resnets")):
             sample = resnet_ref(sd, f"{p}.resnets.{i}", sample, emb)
             if has_attn:
-                sample = transformer2d_ref(sd, f"{p}.attentions.{i}", sample, ctx, head_dim)
+                sample = transformer2d_ref(sd, f"{p}.attentions.{i}", sample, ctx, heads[b])
             res += (sample,)
         if _count(sd, p + ".", "downsamplers") > 0:              # Downsample2D: 3x3 conv, stride 2, padding 1
             sample = _conv(sd, f"{p}.downsamplers.0.conv", sample, stride=2, padding=1)
@@ -121,7 +125,7 @@ def unet_forward_ref(sd, sample, timestep, encoder_hidden_states, mmfs_features=
     # UNetMidBlock2DCrossAttn: resnets[0], then (attention, resnet) pairs
     sample = resnet_ref(sd, "mid_block.resnets.0", sample, emb)
     for i in range(_count(sd, "mid_block.", "attentions")):
-        sample = transformer2d_ref(sd, f"mid_block.attentions.{i}", sample, ctx, head_dim)
+        sample = transformer2d_ref(sd, f"mid_block.attentions.{i}", sample, ctx, heads[-1])
         sample = resnet_ref(sd, f"mid_block.resnets.{i + 1}", sample, emb)
     if mmfs_module is not None:                                   # MODIFICATION START / END of the reference patch
         sample, res = mmfs_module(sample, res, mmfs_features, mmfs_mask)
@@ -135,7 +139,7 @@ def unet_forward_ref(sd, sample, timestep, encoder_hidden_states, mmfs_features=
             sample = torch.cat([sample, skips[-1 - i]], dim=1)    # res_hidden_states_tuple[-1] popped per resnet
             sample = resnet_ref(sd, f"{p}.resnets.{i}", sample, emb)
             if has_attn:
-                sample = transformer2d_ref(sd, f"{p}.attentions.{i}", sample, ctx, head_dim)
+                sample = transformer2d_ref(sd, f"{p}.attentions.{i}", sample, ctx, heads[::-1][b])
         if _count(sd, p + ".", "upsamplers") > 0:                 # Upsample2D: nearest x2, then 3x3 conv
             sample = _conv(sd, f"{p}.upsamplers.0.conv", F.interpolate(sample, scale_factor=2.0, mode="nearest"))
     sample = F.silu(F.group_norm(sample, 32, sd["conv_norm_out.weight"], sd["conv_norm_out.bias"], 1e-5))

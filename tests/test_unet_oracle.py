@@ -82,8 +82,8 @@ def test_tiny_unet_with_mmfs_hook_matches_independent_oracle(use_kernels):
     nsd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     oracle_hook = lambda s, res, f, mk: mmfsnet_ref(nsd, s, list(res), f, mk, downsample_factor=2, n_down=len(res))
     t = torch.tensor(421)
-    want = unet_forward_ref(sd, x, t, ctx, mmfs_features=feats, mmfs_mask=mask, mmfs_module=oracle_hook)
-    want_plain = unet_forward_ref(sd, x, t, ctx)
+    want = unet_forward_ref(sd, x, t, ctx, mmfs_features=feats, mmfs_mask=mask, mmfs_module=oracle_hook, attention_head_dim=(2, 4))
+    want_plain = unet_forward_ref(sd, x, t, ctx, attention_head_dim=(2, 4))
     assert float((want - want_plain).abs().max()) > 1e-3            # the hook is live in the oracle
     old = unet_sd.USE_CONV_KERNEL
     unet_sd.USE_CONV_KERNEL = use_kernels
@@ -122,7 +122,7 @@ def test_full_width_blocks_bf16_kernels_vs_oracle():
     rsd = {"r." + k: bf(v.detach()) for k, v in res.state_dict().items()}
     tsd = {"t." + k: bf(v.detach()) for k, v in tr.state_dict().items()}
     want_r = resnet_ref(rsd, "r", bf(x), bf(temb))
-    want_t = transformer2d_ref(tsd, "t", bf(x), bf(ctx))
+    want_t = transformer2d_ref(tsd, "t", bf(x), bf(ctx), heads=5)
     dt = torch.bfloat16
     with torch.no_grad():
         xin = x.cuda().to(dt).contiguous(memory_format=torch.channels_last)
