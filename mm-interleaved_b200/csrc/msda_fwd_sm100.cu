@@ -313,11 +313,13 @@ static int launch_rows(const void *value, const int64_t *shapes, const int64_t *
     MMFS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 32 * kWarpsPerCta, smem));
     if (ctas_per_sm < 1) { set_error("msda: kernel does not fit on an SM (smem %zu)", smem); return MMFS_EUNSUPPORTED; }
     const int nsm = num_sms();
-    // rows per warp per tile: long enough to amortise staging and keep a CTA on one head, short
-    // enough that every SM gets work; tiny problems (decode, Lq = 1) use 1.
+    // rows per warp per tile: short tiles win on every measured shape (profiles/r01_msda_sweep_v3.json: cfg 3
+    // 144 us at 2 vs 170 us at 8; SD Lq 4096 110 vs 131; Lq 1024 35-40 vs 41): neighbouring q-tiles of one head still
+    // share the L1-resident value slab through the per-SM tile swizzle, and short tiles balance the tail of the
+    // persistent grid.  Tiny problems (decode, Lq = 1) use 1.
     int rpw = g_rows_per_warp;
     if (rpw <= 0) {
-        rpw = 8;
+        rpw = 2;
         while (rpw > 1 && (long)N * M * ((Lq + kWarpsPerCta * rpw - 1) / (kWarpsPerCta * rpw)) < 2L * nsm * ctas_per_sm) rpw >>= 1;
     }
     const int qtiles = (Lq + kWarpsPerCta * rpw - 1) / (kWarpsPerCta * rpw);

@@ -80,6 +80,8 @@ def mmfs_sampler_locw(shapes, starts, qproj, rtable, relpos, refpts, scale_ratio
     return loc, attn, null_mass
 
 
-def set_sampler_tuning(rows_per_warp: int = 0, wmode: int = 1) -> None:
-    """Benchmarks / tests: rows per warp per tile (0 = automatic) and the weight mode of the specialised kernel."""
-    _lib.check(_lib.lib().mmfs_sampler_set_tuning(int(rows_per_warp), int(wmode)), "mmfs_sampler_set_tuning")
+def set_sampler_tuning(rows_per_warp: int = 0, wmode: int = 1, ctas_per_sm: int = 0) -> None:
+    """Benchmarks / tests: rows per warp per tile (0 = automatic), the weight mode of the specialised kernel and the
+    occupancy variant it is compiled for (0 = keep, 3 or 4 resident CTAs per SM)."""
+    _lib.check(_lib.lib().mmfs_sampler_set_tuning(int(rows_per_warp), int(wmode) | (int(ctas_per_sm) << 4)),
+               "mmfs_sampler_set_tuning")

@@ -88,13 +88,14 @@ def test_materialised_locations_and_weights_match_oracle(name):
     assert ((loc.cpu() - inter["sampling_locations"]).abs()[visible]).max() <= 2e-6
     assert (null_mass.cpu() - inter["null_weights"].sum(3).squeeze(-1)).abs().max() <= 2e-6
     # fused gather == un-fused op on the materialised tensors (same taps, same weights)
-    value = mod.project_value(t["input_flatten"].to(DEV))
-    unfused = m.ms_deform_attn_forward(value, t["spatial_shapes"].to(DEV), t["level_start_index"].to(DEV), loc, attn, 1)
-    if value.shape[-1] in (32, 64, 128):
-        fused = m.mmfs_sampler_forward(value, t["spatial_shapes"].to(DEV), t["level_start_index"].to(DEV), qproj, rtable,
-                                       relpos, t["reference_points"].to(DEV).float().contiguous(),
-                                       mod.scale_ratios.float().contiguous(), mod.n_levels, mod.n_points)
-        assert (fused - unfused).abs().max() <= 1e-6
+    with torch.no_grad():                                  # the ctypes kernels are inference-only (ops.inference_only)
+        value = mod.project_value(t["input_flatten"].to(DEV))
+        unfused = m.ms_deform_attn_forward(value, t["spatial_shapes"].to(DEV), t["level_start_index"].to(DEV), loc, attn, 1)
+        if value.shape[-1] in (32, 64, 128):
+            fused = m.mmfs_sampler_forward(value, t["spatial_shapes"].to(DEV), t["level_start_index"].to(DEV), qproj, rtable,
+                                           relpos, t["reference_points"].to(DEV).float().contiguous(),
+                                           mod.scale_ratios.float().contiguous(), mod.n_levels, mod.n_points)
+            assert (fused - unfused).abs().max() <= 1e-6
     # and the index stream of those locations is bit-exact against the oracle's
     from oracle import msda_forward_ref
     _, idx_ref = msda_forward_ref(value.cpu(), t["spatial_shapes"], t["level_start_index"], loc.cpu(), attn.cpu(),
@@ -124,3 +125,19 @@ def test_cpu_tensors_fail_loudly():
     with pytest.raises(RuntimeError, match="CUDA"):
         mod(t["query"], t["reference_points"], t["input_flatten"], t["spatial_shapes"], t["level_start_index"], None,
             t["attention_mask"])
+
+
+def test_kernels_refuse_to_run_where_a_gradient_would_be_dropped():
+    """None of the ctypes kernels is autograd-aware: with grad enabled and a trainable input they raise instead of
+    silently cutting the graph."""
+    params, t, kw, case = load_mmfs_case("llm_tiny")
+    mod = build_module(case, params)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        mod(t["query"].to(DEV), t["reference_points"].to(DEV), t["input_flatten"].to(DEV), t["spatial_shapes"].to(DEV),
+            t["level_start_index"].to(DEV), None, t["attention_mask"].to(DEV))
+    from mm_interleaved_b200 import ops
+    w = torch.nn.Parameter(torch.ones(64, device=DEV))
+    with pytest.raises(RuntimeError, match="inference-only"):
+        ops.rmsnorm(torch.randn((2, 64), device=DEV), w, 1e-6)
+    with torch.no_grad():
+        ops.rmsnorm(torch.randn((2, 64), device=DEV), w, 1e-6)

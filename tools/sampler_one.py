@@ -16,6 +16,7 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 masked = (sys.argv[3] if len(sys.argv) > 3 else "masked") == "masked"
 mode = sys.argv[4] if len(sys.argv) > 4 else "v2"          # v2 (default kernel) | exact | generic | generic_w16
 rpw = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+occ = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 wl = InterleavedCfg3(0, 1, B)
 wl.make_host_inputs(pin=False)
 ids = wl.host[0].cuda()
@@ -35,7 +36,7 @@ ref = torch.full((1, Lq, 1, 2), 0.5, device="cuda")
 scale = torch.tensor([2.0, 1.0, 0.5], device="cuda")
 flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 from mm_interleaved_b200.sampler import set_sampler_tuning  # noqa: E402
-set_sampler_tuning(rpw, 1)
+set_sampler_tuning(rpw, 1, occ)
 kw = dict(v2={}, exact=dict(exact_weights=True), generic=dict(generic=True), generic_w16=dict(generic=True, w16=True))[mode]
 fn = lambda: m.mmfs_sampler_forward(value, shapes, starts, qproj, rtable, relpos, ref, scale, n_lvl, P, **kw)
 for _ in range(3):

@@ -38,10 +38,12 @@ rows = []
 for masked in (True, False):
     cross = cross_attention_mask_from_ids(ids, n_img, 1, wl.SOI_ID) if masked else torch.ones((B, Lq, n_img), device="cuda")
     relpos = _relative_image_index(cross, Lq)
-    for mode, rpws in (("generic", (0,)), ("generic_w16", (0,)), ("exact", (0, 1, 2, 4, 8)), ("v2", (0, 1, 2, 4, 8, 16))):
-        kw = dict(v2={}, exact=dict(exact_weights=True), generic=dict(generic=True), generic_w16=dict(generic=True, w16=True))[mode]
+    for mode, rpws in (("generic", (0,)), ("generic_w16", (0,)), ("exact", (0,)), ("exact_occ4", (0,)), ("v2", (0, 1, 2, 4, 8)),
+                       ("v2_occ4", (0, 1, 2, 4, 8))):
+        kw = dict(v2={}, v2_occ4={}, exact=dict(exact_weights=True), exact_occ4=dict(exact_weights=True), generic=dict(generic=True),
+                  generic_w16=dict(generic=True, w16=True))[mode]
         for rpw in rpws:
-            set_sampler_tuning(rpw, 1)
+            set_sampler_tuning(rpw, 1, 4 if mode.endswith("occ4") else 3)
             fn = lambda: m.mmfs_sampler_forward(value, shapes, starts, qproj, rtable, relpos, ref, scale, n_lvl, P, **kw)
             for _ in range(3):
                 fn()
@@ -57,5 +59,5 @@ for masked in (True, False):
                        us=round(t * 1e6, 1), gbs_8d=round(ab / t / 1e9, 1), frac_hbm=round(ab / t / 1e9 / 6584.5, 4))
             rows.append(row)
             print(row, flush=True)
-set_sampler_tuning(0, 1)
+set_sampler_tuning(0, 1, 3)
 print(json.dumps(rows))

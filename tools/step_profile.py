@@ -12,7 +12,7 @@ from benchmarks import workloads  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else "interleaved_cfg3"
 rows = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 lb = os.environ.get("LOCAL_BATCH")
-wl = workloads.make(name, rank=0, world=1, local_batch=int(lb) if lb else None)
+wl = workloads.make(name, rank=0, world=1, local_batch=int(lb) if lb else 0)
 wl.setup()
 for _ in range(2):
     wl.step_device()
