@@ -726,6 +726,7 @@ class GenerateCfg5(Workload):
     def setup(self):
         self.model = full_model()
         self.model.enable_cuda_graphs(tokenizer=True)
+        self.model.enable_decode_graphs(True)                 # one CUDA graph replay per generated token
         g = torch.Generator().manual_seed(99 + self.rank)
         self.host_sets = []
         for _ in range(2):
@@ -745,6 +746,9 @@ class GenerateCfg5(Workload):
         self._i = 0
         self._text_ms, self._image_ms = [], []
         self.reset_counters()
+
+    def teardown(self):
+        self.model.enable_decode_graphs(False)
 
     def extras(self, value):
         tm = sum(self._text_ms) / len(self._text_ms) if self._text_ms else None
@@ -808,6 +812,7 @@ class GenerateCfg5(Workload):
                             f"out) on one {self.N_IMG}-image / {self.T}-token interleaved context per call (inference.py:237-269)",
                 "step_unit": "one sample: one generate_texts call + one generate_images call (batch 1)",
                 "global_batch": self.world, "seq_len": self.T, "images_per_seq": self.N_IMG, "parallelism": f"dp{self.world}",
+                "cuda_graph": "visual tokenizer graph + one decode-step graph replayed per generated token (enable_decode_graphs)",
                 "l2": "192 MiB buffer written between timed steps"}
 
     def roofline(self, kernel):
