@@ -315,6 +315,7 @@ struct SamplerArgs {
     int rows_per_warp, qtiles;
     long ntiles;
     int ctas_per_sm, nsm, swizzle;
+    int walk_dq, walk_dm, walk_db;   // specialised kernel: grid-stride decomposed into (q-tile, head, batch) steps
 };
 
 

@@ -390,6 +390,7 @@ class _GraphedGreedyDecoder:
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):                                          # lazy handles, weight-derived caches, RoPE tables
+                    self._reset(L, attention_mask, position_ids, cross, logits0)   # every warm-up step is step 0
                     self._step()
             torch.cuda.current_stream().wait_stream(side)
             self._reset(L, attention_mask, position_ids, cross, logits0)
