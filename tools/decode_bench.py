@@ -26,16 +26,18 @@ with torch.no_grad():
     gen = lambda n, **kw: InterleavedForward.generate_texts(model, ids, vis, nimg, wl.N_IMG, max_new_tokens=n, eos_token_id=None, **kw)
 
     def per_token(**kw):
-        best = None
+        """(time of 1 + n_new tokens - time of 1 token) / n_new, each the best of 3 runs (the first run of a shape pays
+        allocations / graph capture)."""
+        t1 = tn = None
         for rep in range(3):
             torch.cuda.synchronize(); t0 = time.time()
             gen(1, **kw)
-            torch.cuda.synchronize(); t1 = time.time()
+            torch.cuda.synchronize(); ta = time.time()
             out = gen(1 + n_new, **kw)
-            torch.cuda.synchronize(); t2 = time.time()
-            v = ((t2 - t1) - (t1 - t0)) / n_new
-            best = v if best is None else min(best, v)
-        return best, 1e3 * (t1 - t0), out
+            torch.cuda.synchronize(); tb = time.time()
+            t1 = (ta - t0) if t1 is None else min(t1, ta - t0)
+            tn = (tb - ta) if tn is None else min(tn, tb - ta)
+        return (tn - t1) / n_new, 1e3 * t1, out
 
     t_eager, pre, out_e = per_token(static_cache=True)
     rows["eager_static_cache_ms_per_token"] = 1e3 * t_eager
