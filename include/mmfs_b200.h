@@ -93,6 +93,17 @@ int mmfs_msda_backward(const void *value, const int64_t *spatial_shapes, const i
                        int N, int S, int M, int D, int L, int Lq, int P, int dtype, void *stream);
 
 /*
+ * Same gradients, run-to-run REPRODUCIBLE: grad_value contributions are accumulated as 64-bit fixed point
+ * with integer atomics (associative => order-independent) and converted to fp32 once.  grad_value_fixed (N,S,M,D) int64
+ * must be ZERO-INITIALISED by the caller; grad_value (N,S,M,D) fp32, grad_loc and grad_attn are fully overwritten;
+ * scratch2 = two device floats (the fixed-point scale derived from max|grad_out| and its inverse).
+ */
+int mmfs_msda_backward_deterministic(const void *value, const int64_t *spatial_shapes, const int64_t *level_start,
+                                     const void *sampling_loc, const void *attn_weight, const void *grad_out,
+                                     long long *grad_value_fixed, float *grad_value, float *grad_loc, float *grad_attn,
+                                     float *scratch2, int N, int S, int M, int D, int L, int Lq, int P, int dtype, void *stream);
+
+/*
  * Integer index stream of the sampler, for parity checking of the sampling-point index
  * math (same device function as the forward kernels use).  idx is int32
  * (N, Lq, M, L, P, 8) = [in_range, h_low, w_low, valid_mask(bit k = corner k+1 fetched),

@@ -29,6 +29,7 @@ SIGNATURES = {
     "mmfs_last_error": (ctypes.c_char_p, []),
     "mmfs_msda_forward": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _U, _P]),
     "mmfs_msda_backward": (_I, [_P] * 9 + [_I] * 8 + [_P]),
+    "mmfs_msda_backward_deterministic": (_I, [_P] * 11 + [_I] * 8 + [_P]),
     "mmfs_msda_index_stream": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "mmfs_msda_forward_host": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _U, _P]),
     "mmfs_release_scratch": (None, []),

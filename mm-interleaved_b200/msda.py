@@ -79,26 +79,45 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
 
 
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
-                            grad_output, im2col_step: int = 64):
+                            grad_output, im2col_step: int = 64, deterministic: bool = True):
     """Drop-in for ``MSDA.ms_deform_attn_backward`` (ops/src/ms_deform_attn.h:41-61): returns
     ``[grad_value, grad_sampling_loc, grad_attn_weight]`` shaped and typed like the inputs.  Gradients are accumulated
     in fp32 and cast back for 16-bit inputs exactly like the reference host code (cu:122-129, 156-160).  fp64 inputs
-    are not implemented (the reference uses them only as ground truth in its test scripts)."""
+    are not implemented (the reference uses them only as ground truth in its test scripts).
+
+    ``deterministic`` (default): ``grad_value`` is reduced with integer atomics on a 64-bit fixed-point buffer, so
+    repeated runs are bit-identical; ``False`` takes the reference's float-atomic scheme (faster,
+    last bits vary with the arrival order of the taps)."""
     N, S, M, D, L, Lq, P = _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step)
     _require(grad_output.is_cuda and grad_output.is_contiguous() and grad_output.dtype == value.dtype and
              tuple(grad_output.shape) == (N, Lq, M * D), "grad_output must be a contiguous CUDA tensor (N, Lq, M*D) of value's dtype")
     if value.dtype == torch.float64:
         raise NotImplementedError("ms_deform_attn_backward: float64 is not implemented on the B200 path")
-    gv = torch.zeros((N, S, M, D), dtype=torch.float32, device=value.device)
     gl = torch.empty((N, Lq, M, L, P, 2), dtype=torch.float32, device=value.device)
     ga = torch.empty((N, Lq, M, L, P), dtype=torch.float32, device=value.device)
-    if N > 0 and Lq > 0:
-        with torch.cuda.device(value.device):
-            rc = _lib.lib().mmfs_msda_backward(
-                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
-                attn_weight.data_ptr(), grad_output.data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr(),
-                N, S, M, D, L, Lq, P, _DTYPE_CODE[value.dtype], torch.cuda.current_stream().cuda_stream)
-        _lib.check(rc, "ms_deform_attn_backward")
+    if deterministic:
+        # grad_value accumulated as 64-bit fixed point with integer atomics: bit-reproducible from run to run
+        gv = torch.empty((N, S, M, D), dtype=torch.float32, device=value.device)
+        fixed = torch.zeros((N, S, M, D), dtype=torch.int64, device=value.device)
+        scratch = torch.empty((2,), dtype=torch.float32, device=value.device)
+        if N > 0 and Lq > 0:
+            with torch.cuda.device(value.device):
+                rc = _lib.lib().mmfs_msda_backward_deterministic(
+                    value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+                    attn_weight.data_ptr(), grad_output.data_ptr(), fixed.data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr(),
+                    scratch.data_ptr(), N, S, M, D, L, Lq, P, _DTYPE_CODE[value.dtype], torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc, "ms_deform_attn_backward (deterministic)")
+        else:
+            gv.zero_()
+    else:
+        gv = torch.zeros((N, S, M, D), dtype=torch.float32, device=value.device)
+        if N > 0 and Lq > 0:
+            with torch.cuda.device(value.device):
+                rc = _lib.lib().mmfs_msda_backward(
+                    value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+                    attn_weight.data_ptr(), grad_output.data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr(),
+                    N, S, M, D, L, Lq, P, _DTYPE_CODE[value.dtype], torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc, "ms_deform_attn_backward")
     return [gv.to(value.dtype), gl.to(value.dtype), ga.to(value.dtype)]
 
 
