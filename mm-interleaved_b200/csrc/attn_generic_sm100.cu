@@ -220,6 +220,107 @@ attn_decode_split_kernel(const T *__restrict__ q, const T *__restrict__ k, const
     }
 }
 
+// hd = 128, 16-bit elements (the Llama decode step): every load is a fully used 16-byte vector.
+//   Q K^T : 8 lanes per key (2 x LDG.128 each = the key's 256 bytes), 4 keys per warp step, 3-shuffle reduction;
+//   P V   : 16 lanes per key (LDG.128 = 8 channels each), 2 keys per warp step, 4 steps in flight.
+// A warp reduces 64 keys in ONE pass (no running rescale) and writes its own (m, l, acc[128]) partial: the merge kernel
+// sees kDecWarps partials per CTA.  (The generic kernel above reads K with 32 different rows per warp instruction --
+// half of every 32-byte sector per load -- and V with 8-byte loads, one key per step: 60 us per layer at the cfg-3 cache.)
+template <typename T>
+__global__ void __launch_bounds__(32 * kDecWarps)
+attn_decode_split128_kernel(const T *__restrict__ q, const T *__restrict__ k, const T *__restrict__ v,
+                            const uint8_t *__restrict__ key_mask, float *__restrict__ part, int H, int Tkv,
+                            long q_bs, long k_bs, long k_ts, long v_bs, long v_ts, float scale, int last_key) {
+    constexpr int HD = 128, KPW = kDecKeys / kDecWarps;          // 64 keys per warp
+    __shared__ float s_p[kDecWarps][KPW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int n_part = gridDim.x * kDecWarps;
+    float *dst = part + (((long)b * H + h) * n_part + split * kDecWarps + warp) * (HD + 2);
+    const int k0 = split * kDecKeys + warp * KPW;
+    if (k0 > last_key) {                                          // nothing for this warp: an empty partial
+        if (lane == 0) { dst[HD] = -INFINITY; dst[HD + 1] = 0.f; }
+        return;
+    }
+    // this lane's 16 channels of q (pre-scaled): channels (lane & 7) * 16 ..
+    const int sub = lane & 7, grp = lane >> 3;
+    float qv[16];
+    {
+        const T *qp = q + b * q_bs + (long)h * HD + sub * 16;
+        float f[8];
+        Vec16<T>::unpack(ldg_nc_v4(qp), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qv[i] = f[i] * scale;
+        Vec16<T>::unpack(ldg_nc_v4(qp + 8), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qv[8 + i] = f[i] * scale;
+    }
+    const T *kb = k + b * k_bs + (long)h * HD + sub * 16;
+    // ---- scores: 16 steps of 4 keys ------------------------------------------------------------------------
+#pragma unroll 4
+    for (int st = 0; st < KPW / 4; ++st) {
+        const int j = k0 + st * 4 + grp;
+        const bool ok = j <= last_key && (key_mask == nullptr || key_mask[(long)b * Tkv + j]);
+        float dot = 0.f;
+        if (ok) {
+            const T *kp = kb + (long)j * k_ts;
+            float f[8];
+            Vec16<T>::unpack(ldg_nc_v4(kp), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dot = fmaf(f[i], qv[i], dot);
+            Vec16<T>::unpack(ldg_nc_v4(kp + 8), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dot = fmaf(f[i], qv[8 + i], dot);
+        }
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+        if (sub == 0) s_p[warp][st * 4 + grp] = ok ? dot : -INFINITY;
+    }
+    __syncwarp();
+    // ---- softmax over the warp's 64 keys ---------------------------------------------------------------------
+    const float s0 = s_p[warp][lane], s1 = s_p[warp][lane + 32];
+    float m = fmaxf(s0, s1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (m == -INFINITY) {                                         // every key of this warp is masked
+        if (lane == 0) { dst[HD] = -INFINITY; dst[HD + 1] = 0.f; }
+        return;
+    }
+    const float p0 = __expf(s0 - m), p1 = __expf(s1 - m);       // masked (-inf) -> 0
+    float l = p0 + p1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    __syncwarp();
+    s_p[warp][lane] = p0;
+    s_p[warp][lane + 32] = p1;
+    __syncwarp();
+    // ---- P V: 32 steps of 2 keys, 16 lanes x 8 channels per key -----------------------------------------------
+    const int half = lane >> 4, ch = (lane & 15) * 8;
+    const T *vb = v + b * v_bs + (long)h * HD + ch;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll 4
+    for (int st = 0; st < KPW / 2; ++st) {
+        const int jj = st * 2 + half;
+        const float pw = s_p[warp][jj];
+        if (pw != 0.f) {                                          // masked / past-the-end keys are never loaded
+            float f[8];
+            Vec16<T>::unpack(ldg_nc_v4(vb + (long)(k0 + jj) * v_ts), f);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = fmaf(pw, f[c], acc[c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 16);
+    if (lane < 16) {
+        *reinterpret_cast<float4 *>(dst + ch) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4 *>(dst + ch + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    if (lane == 0) { dst[HD] = m; dst[HD + 1] = l; }
+}
+
 template <typename T>
 __global__ void attn_decode_merge_kernel(const float *__restrict__ part, T *__restrict__ out, int H, int hd, int n_split,
                                          long o_bs) {
@@ -247,6 +348,15 @@ static int launch_attn_decode(const void *q, const void *k, const void *v, void 
                               float scale, int last_key, cudaStream_t st) {
     const int n_split = (last_key + kDecKeys) / kDecKeys;           // keys 0 .. last_key
     dim3 grid(n_split, H, B);
+    if constexpr (sizeof(T) == 2) {
+        if (hd == 128 && ((uintptr_t)q % 16 == 0) && (q_bs % 8 == 0) && ((uintptr_t)scratch % 16 == 0)) {
+            attn_decode_split128_kernel<T><<<grid, 32 * kDecWarps, 0, st>>>((const T *)q, (const T *)k, (const T *)v, key_mask, scratch, H,
+                                                                         Tkv, q_bs, k_bs, k_ts, v_bs, v_ts, scale, last_key);
+            attn_decode_merge_kernel<T><<<dim3(H, B), 128, 0, st>>>(scratch, (T *)out, H, hd, n_split * kDecWarps, o_bs);
+            MMFS_CUDA(cudaGetLastError());
+            return MMFS_OK;
+        }
+    }
     const size_t smem = (size_t)(hd + kDecWarps * (hd + 2)) * sizeof(float);
     attn_decode_split_kernel<T><<<grid, 32 * kDecWarps, smem, st>>>((const T *)q, (const T *)k, (const T *)v, key_mask, scratch, H,
                                                                    Tkv, hd, q_bs, k_bs, k_ts, v_bs, v_ts, scale, last_key);
@@ -291,7 +401,7 @@ extern "C" int mmfs_attn_generic(const void *q, const void *k, const void *v, vo
 }
 
 extern "C" long mmfs_attn_decode_scratch_floats(int B, int H, int Tkv, int hd) {
-    return (long)B * H * ((Tkv + kDecKeys - 1) / kDecKeys) * (hd + 2);
+    return (long)B * H * ((Tkv + kDecKeys - 1) / kDecKeys) * kDecWarps * (hd + 2);   // one partial per warp (hd 128 path)
 }
 
 extern "C" int mmfs_attn_decode(const void *q, const void *k, const void *v, void *out, const uint8_t *key_mask, float *scratch,
