@@ -314,9 +314,9 @@ attn_decode_split128_kernel(const T *__restrict__ q, const T *__restrict__ k, co
     }
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 16);
-    if (lane < 16) {
-        *reinterpret_cast<float4 *>(dst + ch) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4 *>(dst + ch + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    if (lane < 16) {        // a partial is hd + 2 = 130 floats: 8-byte aligned, not 16
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) *reinterpret_cast<float2 *>(dst + ch + c) = make_float2(acc[c], acc[c + 1]);
     }
     if (lane == 0) { dst[HD] = m; dst[HD + 1] = l; }
 }
