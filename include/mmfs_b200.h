@@ -196,6 +196,22 @@ int mmfs_swiglu(const void *gate_up, void *out, long rows, int inter, int dtype,
  * GELU), on one (rows, 2*inter) buffer holding [value | gate]. */
 int mmfs_geglu(const void *value_gate, void *out, long rows, int inter, int dtype, void *stream);
 
+/* Decode-step linear: y[M, N] = prologue(x)[M, K] . w[N, K]^T (+ residual[M, N]) for M <= 8 rows, f16 / bf16 -- the
+ * q/k/v, o_proj, gate/up and down projections of one generated token (LlamaAttention.forward
+ * decoders/modeling_llama_mmfs.py:217-280, LlamaMLP.forward :188-189) with the operator in front of them folded in:
+ *   prologue 0: x as given;  1: LlamaRMSNorm(x) * norm_weight (:53-70, eps);  2: x is [M, 2K] = [gate | up] and the
+ *   operand is act_fn(gate) * up (:188-189).
+ * residual (may be NULL, may alias y) is added in fp32 before the single rounding of the result.  w rows are streamed
+ * from HBM exactly once (HBM roofline: N * K * sizeof(T) bytes).  N % 8 == 0, K % 256 == 0, all pointers 16-byte aligned,
+ * contiguous rows.  scratch: mmfs_linear_skinny_scratch_floats(N) floats that must be ZERO before the first call; every
+ * call leaves them zero again (arrival tickets of the split between SMs + fp32 partial tiles), so one zeroed buffer of
+ * the largest N serves every call made on one stream.  MMFS_EUNSUPPORTED for shapes outside these limits. */
+long mmfs_linear_skinny_scratch_floats(int N);
+/* measurement hook: largest K chunk per shared-memory stage (columns, 0 = default 2560) and ring depth (0 = default) */
+int mmfs_linear_skinny_set_tuning(int kc_max, int ring_max);
+int mmfs_linear_skinny(const void *x, const void *w, void *y, const void *residual, const void *norm_weight, float *scratch,
+                       int M, int N, int K, int prologue, float eps, int dtype, void *stream);
+
 /*
  * softmax(q k^T * scale + mask) v for decode (q_len = 1 over a KV cache) and small / odd shapes;
  * the tensor-core path for prefill shapes is mmfs_attn_forward.
@@ -209,7 +225,8 @@ int mmfs_attn_generic(const void *q, const void *k, const void *v, void *out, co
                       float scale, int causal, int past, int dtype, void *stream);
 /* Single-query attention over a KV cache (the decode step of generate_texts, q_len = 1), split over the key range:
  * q (B, 1, H, hd) with batch stride q_bs; k / v (B, Tkv, H, hd) views of the cache (row strides in elements, 16-byte
- * aligned rows); out (B, 1, H, hd).  scratch: mmfs_attn_decode_scratch_floats(B, H, Tkv, hd) floats of device memory.
+ * aligned rows); out (B, 1, H, hd).  scratch: mmfs_attn_decode_scratch_floats(B, H, Tkv, hd) floats of device memory,
+ * private to the call until it completes (per-(b, h) arrival tickets, zeroed by the call itself on `stream`, + partials).
  * causal != 0: the query sits at position `past` and sees keys 0..past.  f32 / f16 / bf16, hd % 32 == 0, hd <= 256. */
 long mmfs_attn_decode_scratch_floats(int B, int H, int Tkv, int hd);
 int mmfs_attn_decode(const void *q, const void *k, const void *v, void *out, const uint8_t *key_mask, float *scratch,

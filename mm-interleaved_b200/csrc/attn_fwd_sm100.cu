@@ -60,9 +60,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     uint8_t *s_kmask = reinterpret_cast<uint8_t *>(bars + 14);   // [2][64]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // causal: the CTA scheduler hands out blockIdx.x in increasing order; launching the longest query tiles (most
-    // visible keys) first shortens the tail of the grid
-    const int m_tile = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    // grid = (heads, query tiles, batch), x fastest.  Causal: the CTA scheduler hands blocks out in linear order, so within
+    // one batch entry every head's LONGEST query tile (most visible keys) is issued first and the shortest last —
+    // longest-processing-time-first over the whole batch entry instead of per head (a list-scheduling model of the
+    // cfg-3 grid on 296 slots: 1.13x the ideal makespan per head, 1.01x per batch entry), while the K/V working set of
+    // the resident CTAs stays one batch entry's heads (40 MB at cfg 3, inside L2)
+    const int h = blockIdx.x, b = blockIdx.z;
+    const int m_tile = p.causal ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
     const int q0 = m_tile * kBM;
     // keys this query tile can see: causal -> j <= past + q; never beyond Tkv
     int kv_end = p.Tkv;
@@ -351,7 +355,7 @@ static int launch_attn(const CUtensorMap &mq, const CUtensorMap &mk, const CUten
         MMFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < kMaxDevices) attr_set[dev] = true;
     }
-    dim3 grid((p.Tq + kBM - 1) / kBM, p.H, p.B);
+    dim3 grid(p.H, (p.Tq + kBM - 1) / kBM, p.B);
     kern<<<grid, kAttnThreads, smem, st>>>(mq, mk, mv, p);
     MMFS_CUDA(cudaGetLastError());
     return MMFS_OK;

@@ -15,6 +15,7 @@
 // lane whole keys (row-contiguous 16-byte loads, q broadcast from shared memory), phase 2 gives
 // every lane channels (coalesced V rows), online softmax across chunks.
 #include "common.cuh"
+#include "sampler_common.cuh"   // MixFma (FHFMA)
 
 namespace mmfs {
 
@@ -221,104 +222,183 @@ attn_decode_split_kernel(const T *__restrict__ q, const T *__restrict__ k, const
 }
 
 // hd = 128, 16-bit elements (the Llama decode step): every load is a fully used 16-byte vector.
-//   Q K^T : 8 lanes per key (2 x LDG.128 each = the key's 256 bytes), 4 keys per warp step, 3-shuffle reduction;
-//   P V   : 16 lanes per key (LDG.128 = 8 channels each), 2 keys per warp step, 4 steps in flight.
-// A warp reduces 64 keys in ONE pass (no running rescale) and writes its own (m, l, acc[128]) partial: the merge kernel
-// sees kDecWarps partials per CTA.  (The generic kernel above reads K with 32 different rows per warp instruction --
-// half of every 32-byte sector per load -- and V with 8-byte loads, one key per step: 60 us per layer at the cfg-3 cache.)
+//   Q K^T : 8 lanes per key (2 x LDG.128 each = the key's 256 bytes), 4 keys per warp step; the products are FHFMA
+//           (16-bit k x 16-bit q + fp32 accumulator, exact products, no unpack), the scale is applied to the fp32 dot;
+//   P V   : 16 lanes per key (LDG.128 = 8 channels each), 2 keys per warp step.
+// Loads are issued in explicit BATCHES of eight 16-byte vectors per lane (4 KB per warp), double-buffered in registers,
+// with the key-validity bits balloted once per warp up front: the first version of this kernel tested the mask byte,
+// branched and loaded key by key, which left two loads in flight per warp (SASS: LDG.U8 -> BRA -> 2 x LDG.128 -> SHFL per
+// key; 43 us per layer at the cfg-3 cache = 3.9 TB/s).  A masked key inside the range is still loaded (clamped address)
+// and discarded.
+// A warp reduces 64 keys in one pass (no running rescale); the CTA's four warps are combined in shared memory into one
+// (m, l, acc[128]) partial, and the LAST CTA of a (b, h) to arrive (a ticket per (b, h) in the scratch buffer, zeroed by
+// the launcher) merges the n_split partials and writes the output row -- no second kernel.
 template <typename T>
-__global__ void __launch_bounds__(32 * kDecWarps)
+__device__ __forceinline__ float dot16_mixed(const uint4 &ka, const uint4 &kb, const uint4 &qa, const uint4 &qb) {
+    float d0 = 0.f, d1 = 0.f;
+    const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+    const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        MixFma<T>::fma(d0, (uint16_t)(kw[i] & 0xffffu), (uint16_t)(qw[i] & 0xffffu));
+        MixFma<T>::fma(d1, (uint16_t)(kw[i] >> 16), (uint16_t)(qw[i] >> 16));
+    }
+    return d0 + d1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32 * kDecWarps, 5)
 attn_decode_split128_kernel(const T *__restrict__ q, const T *__restrict__ k, const T *__restrict__ v,
-                            const uint8_t *__restrict__ key_mask, float *__restrict__ part, int H, int Tkv,
-                            long q_bs, long k_bs, long k_ts, long v_bs, long v_ts, float scale, int last_key) {
+                            const uint8_t *__restrict__ key_mask, float *__restrict__ part, unsigned *__restrict__ tickets,
+                            T *__restrict__ out, int H, int Tkv, long q_bs, long k_bs, long k_ts, long v_bs, long v_ts,
+                            long o_bs, float scale, int last_key) {
     constexpr int HD = 128, KPW = kDecKeys / kDecWarps;          // 64 keys per warp
+    static_assert(KPW == 64 && 32 * kDecWarps == HD, "one thread per channel in the combine / merge steps");
     __shared__ float s_p[kDecWarps][KPW];
+    __shared__ __align__(16) float s_acc[kDecWarps][HD];
+    __shared__ float s_m[kDecWarps], s_l[kDecWarps];
+    __shared__ int s_is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int n_part = gridDim.x * kDecWarps;
-    float *dst = part + (((long)b * H + h) * n_part + split * kDecWarps + warp) * (HD + 2);
+    const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z, n_split = gridDim.x;
     const int k0 = split * kDecKeys + warp * KPW;
-    if (k0 > last_key) {                                          // nothing for this warp: an empty partial
-        if (lane == 0) { dst[HD] = -INFINITY; dst[HD + 1] = 0.f; }
-        return;
-    }
-    // this lane's 16 channels of q (pre-scaled): channels (lane & 7) * 16 ..
-    const int sub = lane & 7, grp = lane >> 3;
-    float qv[16];
-    {
-        const T *qp = q + b * q_bs + (long)h * HD + sub * 16;
-        float f[8];
-        Vec16<T>::unpack(ldg_nc_v4(qp), f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) qv[i] = f[i] * scale;
-        Vec16<T>::unpack(ldg_nc_v4(qp + 8), f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) qv[8 + i] = f[i] * scale;
-    }
-    const T *kb = k + b * k_bs + (long)h * HD + sub * 16;
-    // ---- scores: 16 steps of 4 keys ------------------------------------------------------------------------
-#pragma unroll 4
-    for (int st = 0; st < KPW / 4; ++st) {
-        const int j = k0 + st * 4 + grp;
-        const bool ok = j <= last_key && (key_mask == nullptr || key_mask[(long)b * Tkv + j]);
-        float dot = 0.f;
-        if (ok) {
-            const T *kp = kb + (long)j * k_ts;
-            float f[8];
-            Vec16<T>::unpack(ldg_nc_v4(kp), f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dot = fmaf(f[i], qv[i], dot);
-            Vec16<T>::unpack(ldg_nc_v4(kp + 8), f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dot = fmaf(f[i], qv[8 + i], dot);
-        }
-        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-        if (sub == 0) s_p[warp][st * 4 + grp] = ok ? dot : -INFINITY;
-    }
-    __syncwarp();
-    // ---- softmax over the warp's 64 keys ---------------------------------------------------------------------
-    const float s0 = s_p[warp][lane], s1 = s_p[warp][lane + 32];
-    float m = fmaxf(s0, s1);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (m == -INFINITY) {                                         // every key of this warp is masked
-        if (lane == 0) { dst[HD] = -INFINITY; dst[HD + 1] = 0.f; }
-        return;
-    }
-    const float p0 = __expf(s0 - m), p1 = __expf(s1 - m);       // masked (-inf) -> 0
-    float l = p0 + p1;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-    __syncwarp();
-    s_p[warp][lane] = p0;
-    s_p[warp][lane + 32] = p1;
-    __syncwarp();
-    // ---- P V: 32 steps of 2 keys, 16 lanes x 8 channels per key -----------------------------------------------
     const int half = lane >> 4, ch = (lane & 15) * 8;
-    const T *vb = v + b * v_bs + (long)h * HD + ch;
+    float m = -INFINITY, l = 0.f;
     float acc[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-#pragma unroll 4
-    for (int st = 0; st < KPW / 2; ++st) {
-        const int jj = st * 2 + half;
-        const float pw = s_p[warp][jj];
-        if (pw != 0.f) {                                          // masked / past-the-end keys are never loaded
-            float f[8];
-            Vec16<T>::unpack(ldg_nc_v4(vb + (long)(k0 + jj) * v_ts), f);
+
+    unsigned ok_lo = 0u, ok_hi = 0u;                              // validity of keys k0 + 0..31 / k0 + 32..63
+    if (k0 <= last_key) {                                         // warp-uniform
+        const int ja = k0 + lane, jb = ja + 32;
+        const bool oa = ja <= last_key && (key_mask == nullptr || key_mask[(long)b * Tkv + ja]);
+        const bool ob = jb <= last_key && (key_mask == nullptr || key_mask[(long)b * Tkv + jb]);
+        ok_lo = __ballot_sync(0xffffffffu, oa);
+        ok_hi = __ballot_sync(0xffffffffu, ob);
+    }
+    if (ok_lo | ok_hi) {                                          // warp-uniform: at least one visible key
+        const int sub = lane & 7, grp = lane >> 3;
+        const T *qp = q + b * q_bs + (long)h * HD + sub * 16;    // this lane's 16 channels of q, kept packed
+        const uint4 qa = ldg_nc_v4(qp), qb = ldg_nc_v4(qp + 8);
+        const T *kb = k + b * k_bs + (long)h * HD + sub * 16;
+        // Software pipeline over eight batches (K0..K3, V0..V3) with two register buffers: the loads of batch i+1 are
+        // issued BEFORE the arithmetic of batch i, and V0 is requested before the softmax reductions (V does not depend
+        // on P), so every warp keeps one 4 KB batch in flight from its first instruction to its last.  (Without this
+        // a warp has nothing in flight while it computes: ncu r02, 39.8 us, DRAM 54 %, 67 % long-scoreboard stalls.)
+        const T *vb = v + b * v_bs + (long)h * HD + ch;
+        auto load_k = [&](uint4 (&r)[8], int bt) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc[c] = fmaf(pw, f[c], acc[c]);
+            for (int s = 0; s < 4; ++s) {
+                const T *kp = kb + (long)min(k0 + bt * 16 + s * 4 + grp, last_key) * k_ts;
+                r[2 * s] = ldg_nc_v4(kp);
+                r[2 * s + 1] = ldg_nc_v4(kp + 8);
+            }
+        };
+        auto load_v = [&](uint4 (&r)[8], int bt) {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) r[s] = ldg_nc_v4(vb + (long)min(k0 + bt * 16 + s * 2 + half, last_key) * v_ts);
+        };
+        auto scores = [&](const uint4 (&r)[8], int bt) {          // 4 steps of 4 keys
+            const unsigned okw = (bt < 2 ? ok_lo : ok_hi) >> ((bt & 1) * 16);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                float dot = dot16_mixed<T>(r[2 * s], r[2 * s + 1], qa, qb);
+                dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+                dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+                dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+                const bool ok = (okw >> (s * 4 + grp)) & 1u;
+                if (sub == 0) s_p[warp][bt * 16 + s * 4 + grp] = ok ? dot * scale : -INFINITY;
+            }
+        };
+        auto pv = [&](const uint4 (&r)[8], int bt) {              // 8 steps of 2 keys, 16 lanes x 8 channels per key
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const float pw = s_p[warp][bt * 16 + s * 2 + half];
+                if (pw != 0.f) {                                  // a masked slot may hold anything (0 x NaN)
+                    float f[8];
+                    Vec16<T>::unpack(r[s], f);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[c] = fmaf(pw, f[c], acc[c]);
+                }
+            }
+        };
+        uint4 ra[8], rb[8];
+        load_k(ra, 0);
+        load_k(rb, 1); scores(ra, 0);
+        load_k(ra, 2); scores(rb, 1);
+        load_k(rb, 3); scores(ra, 2);
+        load_v(ra, 0); scores(rb, 3);
+        __syncwarp();
+        // ---- softmax over the warp's 64 keys -----------------------------------------------------------------
+        const float s0 = s_p[warp][lane], s1 = s_p[warp][lane + 32];
+        m = fmaxf(s0, s1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float p0 = __expf(s0 - m), p1 = __expf(s1 - m);   // masked (-inf) -> 0; m is finite here
+        l = p0 + p1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+        __syncwarp();
+        s_p[warp][lane] = p0;
+        s_p[warp][lane + 32] = p1;
+        __syncwarp();
+        // ---- P V ---------------------------------------------------------------------------------------------
+        load_v(rb, 1); pv(ra, 0);
+        load_v(ra, 2); pv(rb, 1);
+        load_v(rb, 3); pv(ra, 2);
+        pv(rb, 3);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 16);
+    }
+    if (lane < 16) {
+        *reinterpret_cast<float4 *>(&s_acc[warp][ch]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4 *>(&s_acc[warp][ch + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
+    __syncthreads();
+    // ---- the CTA's partial: thread = channel -------------------------------------------------------------------
+    const int d = threadIdx.x;
+    float M = s_m[0];
+#pragma unroll
+    for (int w = 1; w < kDecWarps; ++w) M = fmaxf(M, s_m[w]);
+    float num = 0.f, den = 0.f;
+    if (M != -INFINITY) {
+#pragma unroll
+        for (int w = 0; w < kDecWarps; ++w) {
+            if (s_m[w] == -INFINITY) continue;
+            const float e = __expf(s_m[w] - M);
+            num = fmaf(e, s_acc[w][d], num);
+            den = fmaf(e, s_l[w], den);
         }
     }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 16);
-    if (lane < 16) {        // a partial is hd + 2 = 130 floats: 8-byte aligned, not 16
-#pragma unroll
-        for (int c = 0; c < 8; c += 2) *reinterpret_cast<float2 *>(dst + ch + c) = make_float2(acc[c], acc[c + 1]);
+    T *orow = out + b * o_bs + (long)h * HD;
+    if (n_split == 1) {                                           // nothing to merge with
+        orow[d] = from_op<T>(den > 0.f ? num / den : 0.f);
+        return;
     }
-    if (lane == 0) { dst[HD] = m; dst[HD + 1] = l; }
+    float *dst = part + (((long)b * H + h) * n_split + split) * (HD + 2);
+    dst[d] = num;
+    if (d == 0) { dst[HD] = M; dst[HD + 1] = den; }
+    __threadfence();                                              // this thread's partial is visible device-wide ...
+    __syncthreads();
+    if (d == 0) s_is_last = atomicAdd(&tickets[b * H + h], 1u) == (unsigned)(n_split - 1);   // ... before the ticket
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+    // ---- last CTA of this (b, h): merge (L2 loads: the partials were written by other SMs) ---------------------
+    const float *p0 = part + ((long)b * H + h) * n_split * (HD + 2);
+    float MM = -INFINITY;
+    for (int s = 0; s < n_split; ++s) MM = fmaxf(MM, __ldcg(p0 + s * (HD + 2) + HD));
+    num = 0.f, den = 0.f;
+    if (MM != -INFINITY) {
+#pragma unroll 4
+        for (int s = 0; s < n_split; ++s) {
+            const float ms = __ldcg(p0 + s * (HD + 2) + HD);
+            const float e = ms == -INFINITY ? 0.f : __expf(ms - MM);
+            num = fmaf(e, __ldcg(p0 + s * (HD + 2) + d), num);
+            den = fmaf(e, __ldcg(p0 + s * (HD + 2) + HD + 1), den);
+        }
+    }
+    orow[d] = from_op<T>(den > 0.f ? num / den : 0.f);           // fully masked row -> zeros
 }
 
 template <typename T>
@@ -342,6 +422,8 @@ __global__ void attn_decode_merge_kernel(const float *__restrict__ part, T *__re
     }
 }
 
+static inline long decode_ticket_floats(int B, int H) { return ((long)B * H + 3) / 4 * 4; }   // keeps the partials 16-byte aligned
+
 template <typename T>
 static int launch_attn_decode(const void *q, const void *k, const void *v, void *out, const uint8_t *key_mask, float *scratch,
                               int B, int H, int Tkv, int hd, long q_bs, long k_bs, long k_ts, long v_bs, long v_ts, long o_bs,
@@ -350,9 +432,12 @@ static int launch_attn_decode(const void *q, const void *k, const void *v, void 
     dim3 grid(n_split, H, B);
     if constexpr (sizeof(T) == 2) {
         if (hd == 128 && ((uintptr_t)q % 16 == 0) && (q_bs % 8 == 0) && ((uintptr_t)scratch % 16 == 0)) {
-            attn_decode_split128_kernel<T><<<grid, 32 * kDecWarps, 0, st>>>((const T *)q, (const T *)k, (const T *)v, key_mask, scratch, H,
-                                                                         Tkv, q_bs, k_bs, k_ts, v_bs, v_ts, scale, last_key);
-            attn_decode_merge_kernel<T><<<dim3(H, B), 128, 0, st>>>(scratch, (T *)out, H, hd, n_split * kDecWarps, o_bs);
+            unsigned *tickets = reinterpret_cast<unsigned *>(scratch);          // [B * H], then the partials
+            float *part = scratch + decode_ticket_floats(B, H);
+            if (n_split > 1) MMFS_CUDA(cudaMemsetAsync(tickets, 0, sizeof(unsigned) * (size_t)B * H, st));
+            attn_decode_split128_kernel<T><<<grid, 32 * kDecWarps, 0, st>>>((const T *)q, (const T *)k, (const T *)v, key_mask, part,
+                                                                         tickets, (T *)out, H, Tkv, q_bs, k_bs, k_ts, v_bs, v_ts,
+                                                                         o_bs, scale, last_key);
             MMFS_CUDA(cudaGetLastError());
             return MMFS_OK;
         }
@@ -401,7 +486,8 @@ extern "C" int mmfs_attn_generic(const void *q, const void *k, const void *v, vo
 }
 
 extern "C" long mmfs_attn_decode_scratch_floats(int B, int H, int Tkv, int hd) {
-    return (long)B * H * ((Tkv + kDecKeys - 1) / kDecKeys) * kDecWarps * (hd + 2);   // one partial per warp (hd 128 path)
+    // tickets [B * H] (hd-128 16-bit path) + one partial per (b, h, split)
+    return decode_ticket_floats(B, H) + (long)B * H * ((Tkv + kDecKeys - 1) / kDecKeys) * (hd + 2);
 }
 
 extern "C" int mmfs_attn_decode(const void *q, const void *k, const void *v, void *out, const uint8_t *key_mask, float *scratch,

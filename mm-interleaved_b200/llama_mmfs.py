@@ -72,6 +72,25 @@ def rotary_tables(dim: int, max_pos: int, base: float = 10000.0, device=None):
     return emb.cos().contiguous(), emb.sin().contiguous()
 
 
+_ROPE_TABLES = {}   # (device, head_dim) -> (n_positions, cos, sin); shared by every layer of every model on the device
+
+
+def shared_rotary_tables(dim: int, need_pos: int, min_pos: int, device):
+    """Tables covering at least ``need_pos`` positions.  One pair per (device, head_dim), grown geometrically: a decode
+    loop that walks past ``max_position_embeddings`` must not rebuild 40 per-layer tables on every token (12 small
+    kernels per layer per token in the round-2 decode profile).  Entries are prefixes of one another (row p depends on
+    p only), so growing never changes a value a captured CUDA graph reads — but the graph holds the OLD storage, which
+    the tuple below keeps alive only until it is replaced; graphed decoders therefore size the table once
+    (need_pos = their static cache length) before capture."""
+    key = (str(device), dim)
+    hit = _ROPE_TABLES.get(key)
+    if hit is None or hit[0] < need_pos:
+        n = max(min_pos, need_pos if hit is None else max(need_pos, 2 * hit[0]))
+        hit = (n,) + rotary_tables(dim, n, device=device)
+        _ROPE_TABLES[key] = hit
+    return hit[1], hit[2]
+
+
 class _CatWeight:
     """Concatenation of several Linear weights along the output dim, rebuilt when a source changes."""
 
@@ -87,6 +106,12 @@ class _CatWeight:
                 self.weight = torch.cat([l.weight for l in self.linears], 0).contiguous()
             self.key = key
         return self.weight
+
+
+def _skinny(x, weight, prologue=0):
+    """Decode-step rows (at most 8 tokens in flight, inference): the linear goes to ``ops.linear_skinny`` -- this repo's
+    HBM-streaming kernel with the RMSNorm / SwiGLU in front folded in -- instead of cuBLAS + a separate kernel."""
+    return (not torch.is_grad_enabled()) and x.is_cuda and ops.linear_skinny_supported(x, weight, prologue)
 
 
 def _addmm_residual(residual, x, weight, inplace):
@@ -110,9 +135,19 @@ class LlamaMLP(nn.Module):
         self.up_proj = nn.Linear(hidden_size, intermediate_size, bias=False)
         self._gate_up = _CatWeight(self.gate_proj, self.up_proj)
 
-    def forward(self, x, residual=None, inplace=False):
-        """``inplace``: accumulate into ``residual``'s storage (beta = 1 GEMM epilogue, no copy of the stream)."""
-        gu = F.linear(x, self._gate_up.get())                 # [gate | up] in one GEMM
+    def forward(self, x, residual=None, inplace=False, pre_norm=None):
+        """``inplace``: accumulate into ``residual``'s storage (beta = 1 GEMM epilogue, no copy of the stream).
+        ``pre_norm`` (extension): the LlamaRMSNorm in front of the block; ``x`` is then the un-normalised stream."""
+        w_gu = self._gate_up.get()
+        inter, hidden = self.down_proj.in_features, self.down_proj.out_features
+        if pre_norm is not None and residual is not None and inplace and _skinny(x, w_gu, 1) and inter % 256 == 0 and \
+                hidden % 8 == 0 and x.shape[:-1].numel() * (inter * 2 + 16) <= 160 * 1024:   # down_proj's own limits
+            gu = ops.linear_skinny(x, w_gu, norm_weight=pre_norm.weight, eps=pre_norm.variance_epsilon)
+            ops.linear_skinny(gu, self.down_proj.weight, residual=residual, out=residual, swiglu=True)
+            return residual
+        if pre_norm is not None:
+            x = pre_norm(x)
+        gu = F.linear(x, w_gu)                                 # [gate | up] in one GEMM
         act = ops.swiglu(gu)
         if residual is None:
             return self.down_proj(act)
@@ -170,21 +205,28 @@ class LlamaAttention(nn.Module):
 
     def rope_tables(self, device, need_pos):
         if self._rope is None or self._rope[0] != device or self._rope[1] < need_pos:
-            n = max(self.max_position_embeddings, need_pos)
-            self._rope = (device, n) + rotary_tables(self.head_dim, n, device=device)
+            cos, sin = shared_rotary_tables(self.head_dim, need_pos, self.max_position_embeddings, device)
+            self._rope = (device, cos.shape[0], cos, sin)
         return self._rope[2], self._rope[3]
 
     def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,
-                output_attentions=False, use_cache=False, residual=None, inplace=False):
+                output_attentions=False, use_cache=False, residual=None, inplace=False, pre_norm=None):
         """``attention_mask``: (B, T_kv) key-padding mask, 1 = attend (what LlamaModel.forward receives,
         modeling_llama_mmfs.py:625) or None.  Causality is implicit (decoder).  Returns
         (attn_output [+ residual], None, present_key_value) like the reference (:217-280); the cache
-        holds (key, value) in (B, T, H, hd) layout."""
+        holds (key, value) in (B, T, H, hd) layout.  ``pre_norm`` (extension): the input LlamaRMSNorm;
+        ``hidden_states`` is then the un-normalised stream (a decode step folds the norm into the q/k/v kernel)."""
         if output_attentions:
             raise NotImplementedError("attention probabilities are never materialised by the fused kernel")
         B, T, _ = hidden_states.shape
         H, hd = self.num_heads, self.head_dim
-        qkv = F.linear(hidden_states, self._qkv.get()).view(B, T, 3, H, hd)
+        w_qkv = self._qkv.get()
+        skinny = _skinny(hidden_states, w_qkv, 1 if pre_norm is not None else 0)
+        if skinny:
+            qkv = ops.linear_skinny(hidden_states, w_qkv, norm_weight=None if pre_norm is None else pre_norm.weight,
+                                    eps=0.0 if pre_norm is None else pre_norm.variance_epsilon).view(B, T, 3, H, hd)
+        else:
+            qkv = F.linear(hidden_states if pre_norm is None else pre_norm(hidden_states), w_qkv).view(B, T, 3, H, hd)
         q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
         static = isinstance(past_key_value, StaticKV)
         past = 0 if past_key_value is None else (past_key_value.length if static else past_key_value[0].shape[1])
@@ -220,7 +262,10 @@ class LlamaAttention(nn.Module):
             else:
                 key_mask = attention_mask
         ctx = ops.attention(q, k, v, key_mask=key_mask, causal=True, past=past)       # (B, T, H*hd)
-        out = self.o_proj(ctx) if residual is None else _addmm_residual(residual, ctx, self.o_proj.weight, inplace)
+        if skinny and residual is not None and inplace and _skinny(ctx, self.o_proj.weight):
+            out = ops.linear_skinny(ctx, self.o_proj.weight, residual=residual, out=residual)
+        else:
+            out = self.o_proj(ctx) if residual is None else _addmm_residual(residual, ctx, self.o_proj.weight, inplace)
         return out, None, present
 
 
@@ -325,15 +370,13 @@ class LlamaDecoderLayer(nn.Module):
         # guarantees ``hidden_states`` is a private contiguous buffer (LlamaModel.forward clones the embeddings once).
         residual = hidden_states.contiguous()
         inplace = inplace and not torch.is_grad_enabled()
-        h = self.input_layernorm(residual)
-        hidden_states, _, present = self.self_attn(h, attention_mask=attention_mask, position_ids=position_ids,
+        hidden_states, _, present = self.self_attn(residual, attention_mask=attention_mask, position_ids=position_ids,
                                                    past_key_value=past_key_value, use_cache=use_cache, residual=residual,
-                                                   inplace=inplace)
+                                                   inplace=inplace, pre_norm=self.input_layernorm)
         if self.llama_cross_attn is not None and vision_hidden_states is not None:
             hidden_states = self.llama_cross_attn(hidden_states, vision_hidden_states, cross_attention_mask,
                                                   residual=hidden_states, inplace=inplace)
-        h = self.post_attention_layernorm(hidden_states)
-        hidden_states = self.mlp(h, residual=hidden_states, inplace=inplace)
+        hidden_states = self.mlp(hidden_states, residual=hidden_states, inplace=inplace, pre_norm=self.post_attention_layernorm)
         outputs = (hidden_states,)
         if use_cache:
             outputs += (present,)

@@ -399,6 +399,9 @@ class _GraphedGreedyDecoder:
             with torch.cuda.graph(self.graph):
                 self._step()
             self.launches = ops.launch_counter[0] - before
+            # the graph reads the RoPE tables by address: keep the captured storage alive even if an eager decode grows
+            # (and so replaces) the shared tables later
+            self._captured_rope = [l.self_attn._rope for l in o.mm_decoder.layers]
             for c in self.past:                                             # the warm-up steps wrote slots L, L+1
                 c.k[:, L:].zero_()
                 c.v[:, L:].zero_()

@@ -119,3 +119,8 @@ def test_decode_attention_matches_eager(case, dtype):
         km0 = km.clone(); km0[1] = 0
         z = ops.attention(q, k, v, key_mask=km0, causal=True, past=Tkv - 1).view(B, 1, H, hd)
         assert torch.count_nonzero(z[1]) == 0 and torch.isfinite(z.float()).all()
+        # masked cache slots may hold anything (the graphed decoder attends its whole static buffer): NaN there must not leak
+        kc2, vc2 = kc.clone(), vc.clone()
+        kc2[0, :260] = float("nan"); vc2[0, :260] = float("inf"); kc2[-1, 3:9] = float("nan"); vc2[-1, 3:9] = float("nan")
+        o2 = ops.attention(q, kc2[:, :Tkv], vc2[:, :Tkv], key_mask=km, causal=True, past=Tkv - 1).view(B, 1, H, hd)
+        assert torch.equal(o2, out)
