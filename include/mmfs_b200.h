@@ -202,13 +202,11 @@ int mmfs_geglu(const void *value_gate, void *out, long rows, int inter, int dtyp
  *   prologue 0: x as given;  1: LlamaRMSNorm(x) * norm_weight (:53-70, eps);  2: x is [M, 2K] = [gate | up] and the
  *   operand is act_fn(gate) * up (:188-189).
  * residual (may be NULL, may alias y) is added in fp32 before the single rounding of the result.  w rows are streamed
- * from HBM exactly once (HBM roofline: N * K * sizeof(T) bytes).  N % 8 == 0, K % 256 == 0, all pointers 16-byte aligned,
+ * from HBM exactly once (HBM roofline: N * K * sizeof(T) bytes).  N % 32 == 0, K % 512 == 0, all pointers 16-byte aligned,
  * contiguous rows.  scratch: mmfs_linear_skinny_scratch_floats(N) floats that must be ZERO before the first call; every
  * call leaves them zero again (arrival tickets of the split between SMs + fp32 partial tiles), so one zeroed buffer of
  * the largest N serves every call made on one stream.  MMFS_EUNSUPPORTED for shapes outside these limits. */
 long mmfs_linear_skinny_scratch_floats(int N);
-/* measurement hook: largest K chunk per shared-memory stage (columns, 0 = default 2560) and ring depth (0 = default) */
-int mmfs_linear_skinny_set_tuning(int kc_max, int ring_max);
 int mmfs_linear_skinny(const void *x, const void *w, void *y, const void *residual, const void *norm_weight, float *scratch,
                        int M, int N, int K, int prologue, float eps, int dtype, void *stream);
 

@@ -21,6 +21,7 @@ Plain library GEMMs (cuBLAS via torch) are used for the dense linears.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from types import SimpleNamespace
 from typing import List, Optional, Tuple
@@ -108,10 +109,16 @@ class _CatWeight:
         return self.weight
 
 
+# Decode-step linears (at most 8 tokens in flight): ``ops.linear_skinny`` -- this repo's HBM-streaming kernel with the
+# RMSNorm / SwiGLU in front folded in -- or cuBLAS + the stand-alone norm / activation kernel.  Measured on the 13 B
+# decoder at batch 4 (profiles/r02_skinny_linear_ab.log): 151 us per layer against 130 us for cuBLAS, so cuBLAS stays the
+# default; MMFS_SKINNY_LINEARS=1 or ``llama_mmfs.SKINNY_DECODE_LINEARS = True`` switches.
+SKINNY_DECODE_LINEARS = os.environ.get("MMFS_SKINNY_LINEARS", "0") == "1"
+
+
 def _skinny(x, weight, prologue=0):
-    """Decode-step rows (at most 8 tokens in flight, inference): the linear goes to ``ops.linear_skinny`` -- this repo's
-    HBM-streaming kernel with the RMSNorm / SwiGLU in front folded in -- instead of cuBLAS + a separate kernel."""
-    return (not torch.is_grad_enabled()) and x.is_cuda and ops.linear_skinny_supported(x, weight, prologue)
+    return (SKINNY_DECODE_LINEARS and not torch.is_grad_enabled() and x.is_cuda and
+            ops.linear_skinny_supported(x, weight, prologue))
 
 
 def _addmm_residual(residual, x, weight, inplace):
@@ -140,8 +147,8 @@ class LlamaMLP(nn.Module):
         ``pre_norm`` (extension): the LlamaRMSNorm in front of the block; ``x`` is then the un-normalised stream."""
         w_gu = self._gate_up.get()
         inter, hidden = self.down_proj.in_features, self.down_proj.out_features
-        if pre_norm is not None and residual is not None and inplace and _skinny(x, w_gu, 1) and inter % 256 == 0 and \
-                hidden % 8 == 0 and x.shape[:-1].numel() * (inter * 2 + 16) <= 160 * 1024:   # down_proj's own limits
+        if pre_norm is not None and residual is not None and inplace and _skinny(x, w_gu, 1) and \
+                ops.linear_skinny_shape_ok(x.shape[:-1].numel(), hidden, inter):           # down_proj's own limits
             gu = ops.linear_skinny(x, w_gu, norm_weight=pre_norm.weight, eps=pre_norm.variance_epsilon)
             ops.linear_skinny(gu, self.down_proj.weight, residual=residual, out=residual, swiglu=True)
             return residual

@@ -151,15 +151,19 @@ def attention(q, k, v, key_mask=None, causal=True, past=0, scale=None, force_gen
 _SKINNY_SCRATCH = {}   # device -> zeroed fp32 scratch (tickets + partial tiles), shared by every call on the device
 
 
+def linear_skinny_shape_ok(M: int, N: int, K: int) -> bool:
+    """At most 8 rows, N % 32 == 0, K % 512 == 0, the x rows + at least two 32 KB stages of the copy ring inside shared
+    memory (``csrc/linear_skinny_sm100.cu``): 8 rows up to K = 9216, 4 rows up to K = 18432."""
+    return (1 <= M <= 8 and N % 32 == 0 and N <= 32 << 16 and K % 512 == 0 and
+            2 * 32768 + M * (K * 2 + 64) + 16912 <= 227 * 1024)
+
+
 def linear_skinny_supported(x: torch.Tensor, weight: torch.Tensor, prologue: int = 0) -> bool:
-    """Shapes ``linear_skinny`` takes: at most 8 rows, 16-bit, N % 8 == 0, K % 256 == 0, x rows + a 3-stage weight ring
-    inside shared memory (``csrc/linear_skinny_sm100.cu``)."""
+    """Whether ``linear_skinny`` takes this call: CUDA, f16 / bf16, contiguous, ``linear_skinny_shape_ok``."""
     N, K = weight.shape
     M = x.numel() // (K * (2 if prologue == 2 else 1))
-    if not (x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and weight.dtype == x.dtype and x.is_contiguous()
-            and weight.is_contiguous() and 1 <= M <= 8 and N % 8 == 0 and K % 256 == 0):
-        return False
-    return M * (K * 2 + 16) + 3 * 8 * (256 * 2 + 16) + 5000 <= 227 * 1024
+    return (x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and weight.dtype == x.dtype and x.is_contiguous()
+            and weight.is_contiguous() and linear_skinny_shape_ok(M, N, K))
 
 
 def linear_skinny(x: torch.Tensor, weight: torch.Tensor, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,

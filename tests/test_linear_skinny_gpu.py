@@ -12,10 +12,10 @@ CASES = [
     (4, 5120, 5120, 0, True),       # o_proj + residual (blocks cut by range boundaries: 320 blocks on 148 SMs)
     (4, 27648, 5120, 1, False),     # gate | up with the post-attention RMSNorm
     (4, 5120, 13824, 2, True),      # down_proj of silu(gate) * up, + residual
-    (1, 2368, 512, 0, False),       # one stage per block
+    (1, 4736, 512, 0, False),       # one step per block
     (8, 1024, 1024, 1, True),       # 8 rows
-    (3, 48, 512, 2, False),         # fewer blocks than SMs
-    (2, 64, 256, 0, True),          # the smallest K
+    (3, 96, 512, 2, False),         # fewer blocks than SMs
+    (8, 5120, 5120, 0, True),       # 8 rows at the decoder's width
 ]
 
 
@@ -69,10 +69,11 @@ def test_linear_skinny_rejects_what_it_cannot_take():
     from mm_interleaved_b200 import ops
     x = torch.zeros((9, 512), dtype=torch.bfloat16, device=DEV)
     w = torch.zeros((64, 512), dtype=torch.bfloat16, device=DEV)
+    assert not ops.linear_skinny_supported(x[:4], torch.zeros((40, 512), dtype=torch.bfloat16, device=DEV))
     assert not ops.linear_skinny_supported(x, w)
     with pytest.raises(RuntimeError):
         ops.linear_skinny(x, w)
-    assert not ops.linear_skinny_supported(x[:4], torch.zeros((64, 500), dtype=torch.bfloat16, device=DEV))
+    assert not ops.linear_skinny_supported(x[:4], torch.zeros((64, 768), dtype=torch.bfloat16, device=DEV))
     assert not ops.linear_skinny_supported(x[:4].float(), w.float())
 
 
@@ -90,9 +91,8 @@ def test_decode_step_with_folded_linears_matches_the_cublas_path():
     emb = torch.randn((B, T, 512), device=DEV).to(torch.bfloat16)
     outs = []
     for disabled in (False, True):
-        saved = llama_mmfs._skinny
-        if disabled:
-            llama_mmfs._skinny = lambda *a, **k: False
+        saved = llama_mmfs.SKINNY_DECODE_LINEARS
+        llama_mmfs.SKINNY_DECODE_LINEARS = not disabled
         try:
             before = ops.launch_counter[0]
             with torch.no_grad():
@@ -104,7 +104,7 @@ def test_decode_step_with_folded_linears_matches_the_cublas_path():
                     steps.append(o)
             outs.append((torch.cat(steps, 1).float(), ops.launch_counter[0] - before))
         finally:
-            llama_mmfs._skinny = saved
+            llama_mmfs.SKINNY_DECODE_LINEARS = saved
     (a, n_a), (b, n_b) = outs
     assert n_a != n_b                                   # the folded path really ran (different kernel count)
     assert (a - b).abs().max() <= 3e-2 * b.abs().max()

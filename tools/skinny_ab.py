@@ -46,10 +46,6 @@ def timed(fn, reps=15):
     return ts[len(ts) // 2]
 
 
-from mm_interleaved_b200 import _lib  # noqa: E402
-KC, RING = int(os.environ.get("KC_MAX", 0)), int(os.environ.get("RING_MAX", 0))
-assert _lib.lib().mmfs_linear_skinny_set_tuning(KC, RING) == 0
-print(f"kc_max = {KC or 2560}, ring_max = {RING or 12}")
 tot_a = tot_b = 0.0
 with torch.no_grad():
     for name, N, K, pro, with_res in SHAPES:
