@@ -191,6 +191,15 @@ int mmfs_layernorm(const void *x, const void *weight, const void *bias, void *y,
 int mmfs_rope_qk(void *q, void *k, const float *cos_table, const float *sin_table, const int64_t *position_ids,
                  long n_tokens, int T_len, int H, int hd, int q_stride, int k_stride, int pos_per_batch,
                  int dtype, void *stream);
+/* RoPE + KV-cache append in one pass (static-cache extension of LlamaAttention.forward, modeling_llama_mmfs.py:230-239):
+ * q (n_tokens rows, q_stride elements apart, H x hd dense) is rotated in place; the rotated k and the v of token t of
+ * batch entry b are written to row (slot + t) of k_cache / v_cache ((B, T_max, H, hd), batch / row strides cache_bs /
+ * cache_ts in elements).  slot = *slot_dev when slot_dev != NULL (device int64: the graphed decode step), else slot_host.
+ * The k operand itself is left unrotated. */
+int mmfs_rope_qk_append(void *q, const void *k, const void *v, const float *cos_table, const float *sin_table,
+                        const int64_t *position_ids, void *k_cache, void *v_cache, const int64_t *slot_dev, long slot_host,
+                        long n_tokens, int T_len, int H, int hd, int q_stride, int k_stride, int v_stride, long cache_bs,
+                        long cache_ts, int pos_per_batch, int dtype, void *stream);
 int mmfs_swiglu(const void *gate_up, void *out, long rows, int inter, int dtype, void *stream);
 /* GEGLU of the SD-UNet feed-forward (diffusers GEGLU: hidden, gate = proj(x).chunk(2); hidden * gelu(gate), exact erf
  * GELU), on one (rows, 2*inter) buffer holding [value | gate]. */

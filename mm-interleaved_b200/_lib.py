@@ -40,6 +40,7 @@ SIGNATURES = {
     "mmfs_rmsnorm": (_I, [_P, _P, _P, _L, _I, _F, _I, _P]),
     "mmfs_layernorm": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P]),
     "mmfs_rope_qk": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "mmfs_rope_qk_append": (_I, [_P] * 9 + [_L, _L] + [_I] * 6 + [_L, _L, _I, _I, _P]),
     "mmfs_swiglu": (_I, [_P, _P, _L, _I, _I, _P]),
     "mmfs_geglu": (_I, [_P, _P, _L, _I, _I, _P]),
     "mmfs_linear_skinny_scratch_floats": (_L, [_I]),

@@ -247,6 +247,62 @@ __global__ void __launch_bounds__(256) rope_qk_kernel(T *__restrict__ q, T *__re
     }
 }
 
+// RoPE + KV-cache append in one pass (extension; a static cache replaces the reference's torch.cat append,
+// modeling_llama_mmfs.py:236-239): q is rotated in place, the ROTATED k and the v of every token go straight into
+// the cache row of the token -- row (slot + t) of batch entry b, where slot is a host integer (prefill / eager decode:
+// the number of positions already cached) or is read from device memory (the graphed decode step).  Same arithmetic
+// as rope_qk_kernel; saves the in-place write of k plus two copy kernels per layer and token.
+template <typename T>
+__global__ void __launch_bounds__(256) rope_append_kernel(T *__restrict__ q, const T *__restrict__ k, const T *__restrict__ v,
+                                                           const float *__restrict__ cos_t, const float *__restrict__ sin_t,
+                                                           const int64_t *__restrict__ pos, T *__restrict__ k_cache,
+                                                           T *__restrict__ v_cache, const int64_t *__restrict__ slot_dev,
+                                                           long slot_host, long n_tok, int H, int hd, int q_stride, int k_stride,
+                                                           int v_stride, long cache_bs, long cache_ts, int pos_per_batch, int T_len) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const int half = hd >> 1;
+    const int chunks = half / VEC;
+    const int n_rot = 2 * H * chunks;                     // rotation items: q heads then k heads
+    const int n_copy = H * hd / VEC;                      // v vectors
+    const long slot = slot_dev != nullptr ? (long)*slot_dev : slot_host;
+    for (long tok = blockIdx.x; tok < n_tok; tok += gridDim.x) {
+        const long p = pos[pos_per_batch ? tok : (tok % T_len)];
+        const float *cp = cos_t + p * hd, *sp = sin_t + p * hd;
+        const long b = tok / T_len, tt = tok - b * T_len;
+        T *qt = q + tok * q_stride;
+        const T *kt = k + tok * k_stride, *vt = v + tok * v_stride;
+        T *kc = k_cache + b * cache_bs + (slot + tt) * cache_ts, *vc = v_cache + b * cache_bs + (slot + tt) * cache_ts;
+        for (int it = threadIdx.x; it < n_rot + n_copy; it += blockDim.x) {
+            if (it >= n_rot) {                            // v: plain copy
+                const int i = (it - n_rot) * VEC;
+                *reinterpret_cast<uint4 *>(vc + i) = *reinterpret_cast<const uint4 *>(vt + i);
+                continue;
+            }
+            const int c = it % chunks, hh = it / chunks;
+            const bool is_k = hh >= H;
+            const T *src = (is_k ? kt + (size_t)(hh - H) * hd : qt + (size_t)hh * hd) + c * VEC;
+            T *dst = (is_k ? kc + (size_t)(hh - H) * hd : qt + (size_t)hh * hd) + c * VEC;
+            float cs[VEC], sn[VEC], x1[VEC], x2[VEC], o1[VEC], o2[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; i += 4) {
+                const float4 a = *reinterpret_cast<const float4 *>(cp + c * VEC + i);
+                const float4 bb = *reinterpret_cast<const float4 *>(sp + c * VEC + i);
+                cs[i] = rnd<T>(a.x); cs[i + 1] = rnd<T>(a.y); cs[i + 2] = rnd<T>(a.z); cs[i + 3] = rnd<T>(a.w);
+                sn[i] = rnd<T>(bb.x); sn[i + 1] = rnd<T>(bb.y); sn[i + 2] = rnd<T>(bb.z); sn[i + 3] = rnd<T>(bb.w);
+            }
+            Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(src), x1);
+            Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(src + half), x2);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                o1[i] = rnd<T>(x1[i] * cs[i]) + rnd<T>(-x2[i] * sn[i]);
+                o2[i] = rnd<T>(x2[i] * cs[i]) + rnd<T>(x1[i] * sn[i]);
+            }
+            *reinterpret_cast<uint4 *>(dst) = Vec16<T>::pack(o1);
+            *reinterpret_cast<uint4 *>(dst + half) = Vec16<T>::pack(o2);
+        }
+    }
+}
+
 // silu in fp32: exact expf / division for fp32 tensors; ex2.approx + rcp.approx for 16-bit tensors, whose result is
 // rounded to 8 / 11 significand bits right after (relative error of the fast path ~2^-21).
 template <typename T> __device__ __forceinline__ float silu_op(float g) { return __fdividef(g, 1.f + __expf(-g)); }
@@ -383,6 +439,42 @@ extern "C" int mmfs_rope_qk(void *q, void *k, const float *cos_table, const floa
                    "rope_qk: head_dim/2 must be a multiple of the 16-byte vector and rows 16-byte aligned");
     return dispatch(dtype, 2, k, nullptr, position_ids, q, cos_table, sin_table, n_tokens, H, hd, q_stride, k_stride,
                     pos_per_batch, T_len, 0.f, stream);
+}
+
+template <typename T>
+static int launch_rope_append(void *q, const void *k, const void *v, const float *cos_t, const float *sin_t, const int64_t *pos,
+                              void *kc, void *vc, const int64_t *slot_dev, long slot_host, long n_tok, int T_len, int H, int hd,
+                              int qs, int ks, int vs, long cbs, long cts, int ppb, cudaStream_t st) {
+    const int items = H * ((hd / 2) / (16 / (int)sizeof(T))) * 2 + H * hd / (16 / (int)sizeof(T));
+    const int threads = items >= 256 ? 256 : ((items + 31) / 32) * 32;
+    const int grid = (int)(n_tok < 148L * 32 ? n_tok : 148L * 32);
+    rope_append_kernel<T><<<grid, threads, 0, st>>>((T *)q, (const T *)k, (const T *)v, cos_t, sin_t, pos, (T *)kc, (T *)vc, slot_dev,
+                                                 slot_host, n_tok, H, hd, qs, ks, vs, cbs, cts, ppb, T_len);
+    MMFS_CUDA(cudaGetLastError());
+    return MMFS_OK;
+}
+
+extern "C" int mmfs_rope_qk_append(void *q, const void *k, const void *v, const float *cos_table, const float *sin_table,
+                                   const int64_t *position_ids, void *k_cache, void *v_cache, const int64_t *slot_dev,
+                                   long slot_host, long n_tokens, int T_len, int H, int hd, int q_stride, int k_stride,
+                                   int v_stride, long cache_bs, long cache_ts, int pos_per_batch, int dtype, void *stream) {
+    MMFS_CHECK_ARG(n_tokens >= 0 && H > 0 && hd > 0 && hd % 2 == 0 && T_len > 0 && slot_host >= 0, "rope_qk_append: bad shape");
+    if (n_tokens == 0) return MMFS_OK;
+    MMFS_CHECK_ARG(q && k && v && cos_table && sin_table && position_ids && k_cache && v_cache, "rope_qk_append: null pointer argument");
+    const size_t es = dtype_size(dtype);
+    MMFS_CHECK_ARG(es == 2 || es == 4, "rope_qk_append: f32 / f16 / bf16");
+    MMFS_CHECK_ARG((hd / 2) % (16 / (int)es) == 0 &&
+                       ((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)k_cache | (uintptr_t)v_cache) % 16 == 0 &&
+                       (q_stride * es) % 16 == 0 && (k_stride * es) % 16 == 0 && (v_stride * es) % 16 == 0 &&
+                       (cache_bs * es) % 16 == 0 && (cache_ts * es) % 16 == 0,
+                   "rope_qk_append: head_dim/2 must be a multiple of the 16-byte vector and all rows 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case MMFS_F32: return launch_rope_append<float>(q, k, v, cos_table, sin_table, position_ids, k_cache, v_cache, slot_dev, slot_host, n_tokens, T_len, H, hd, q_stride, k_stride, v_stride, cache_bs, cache_ts, pos_per_batch, st);
+        case MMFS_F16: return launch_rope_append<__half>(q, k, v, cos_table, sin_table, position_ids, k_cache, v_cache, slot_dev, slot_host, n_tokens, T_len, H, hd, q_stride, k_stride, v_stride, cache_bs, cache_ts, pos_per_batch, st);
+        case MMFS_BF16: return launch_rope_append<__nv_bfloat16>(q, k, v, cos_table, sin_table, position_ids, k_cache, v_cache, slot_dev, slot_host, n_tokens, T_len, H, hd, q_stride, k_stride, v_stride, cache_bs, cache_ts, pos_per_batch, st);
+        default: set_error("rope_qk_append: dtype %d unsupported", dtype); return MMFS_EINVAL;
+    }
 }
 
 extern "C" int mmfs_swiglu(const void *gate_up, void *out, long rows, int inter, int dtype, void *stream) {

@@ -240,24 +240,22 @@ class LlamaAttention(nn.Module):
         if position_ids is None:
             position_ids = torch.arange(past, past + T, device=hidden_states.device)
         cos, sin = self.rope_tables(hidden_states.device, past + T)
-        ops.rope_qk_(q, k, cos, sin, position_ids)
         if static and past_key_value.slot is not None:          # graph decode: device-side slot, whole buffer visible
             if T != 1:
                 raise RuntimeError("StaticKV.slot (graph decode) takes one token per step")
-            past_key_value.k.index_copy_(1, past_key_value.slot, k)
-            past_key_value.v.index_copy_(1, past_key_value.slot, v)
+            ops.rope_qk_append_(q, k, v, cos, sin, position_ids, past_key_value.k, past_key_value.v, past_key_value.slot)
             k, v = past_key_value.k, past_key_value.v
             past = k.shape[1] - 1
             present = past_key_value
         elif static:
             if past + T > past_key_value.k.shape[1]:
                 raise RuntimeError(f"StaticKV of {past_key_value.k.shape[1]} positions cannot take {past} + {T}")
-            past_key_value.k[:, past:past + T].copy_(k)
-            past_key_value.v[:, past:past + T].copy_(v)
-            past_key_value.length = past + T
+            ops.rope_qk_append_(q, k, v, cos, sin, position_ids, past_key_value.k, past_key_value.v, past)   # one kernel:
+            past_key_value.length = past + T                                   # RoPE + both cache writes
             k, v = past_key_value.k[:, :past + T], past_key_value.v[:, :past + T]
             present = past_key_value
         else:
+            ops.rope_qk_(q, k, cos, sin, position_ids)
             if past_key_value is not None:
                 k = torch.cat([past_key_value[0], k], dim=1)
                 v = torch.cat([past_key_value[1], v], dim=1)

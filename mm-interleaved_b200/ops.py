@@ -75,6 +75,40 @@ def rope_qk_(q: torch.Tensor, k: torch.Tensor, cos: torch.Tensor, sin: torch.Ten
     launch_counter[0] += 1
 
 
+def rope_qk_append_(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor,
+                    position_ids: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, slot) -> None:
+    """``rope_qk_`` + the append to a static KV cache in one kernel: q rotated in place; rotated k and v of token t of
+    batch entry b written to ``k_cache[b, slot + t]`` / ``v_cache[b, slot + t]``.  ``slot``: int (positions already
+    cached) or a (1,) int64 CUDA tensor read by the kernel (graphed decode).  ``k`` itself is left unrotated."""
+    B, T, H, hd = q.shape
+    inference_only("rope_qk_append_", q, k, v)
+    for t in (q, k, v):
+        _require(t.is_cuda and tuple(t.shape) == (B, T, H, hd) and t.stride(3) == 1 and t.stride(2) == hd and
+                 t.stride(0) == T * t.stride(1), "rope_qk_append_: q / k / v must be (B,T,H,hd) with dense heads and uniform token stride")
+    for c in (k_cache, v_cache):
+        _require(c.is_cuda and c.dim() == 4 and c.shape[0] == B and tuple(c.shape[2:]) == (H, hd) and c.stride(3) == 1 and
+                 c.stride(2) == hd and c.dtype == q.dtype, "rope_qk_append_: caches must be (B, T_max, H, hd), dense heads")
+    _require(k_cache.stride() == v_cache.stride(), "rope_qk_append_: k / v caches must share their strides")
+    _require(cos.dtype == torch.float32 and sin.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous()
+             and cos.shape[-1] == hd, "rope_qk_append_: cos / sin must be contiguous fp32 (max_pos, hd)")
+    pos = position_ids.to(torch.int64).contiguous()
+    per_batch = 1 if pos.numel() == B * T else 0
+    _require(per_batch or pos.numel() == T, "rope_qk_append_: position_ids must have B*T or T entries")
+    if isinstance(slot, torch.Tensor):
+        _require(slot.is_cuda and slot.dtype == torch.int64 and slot.numel() == 1, "rope_qk_append_: slot tensor must be (1,) int64 on the device")
+        slot_dev, slot_host = slot.data_ptr(), 0
+    else:
+        slot_dev, slot_host = None, int(slot)
+        _require(0 <= slot_host and slot_host + T <= k_cache.shape[1], "rope_qk_append_: slot + T exceeds the cache")
+    with torch.cuda.device(q.device):
+        rc = _lib.lib().mmfs_rope_qk_append(q.data_ptr(), k.data_ptr(), v.data_ptr(), cos.data_ptr(), sin.data_ptr(), pos.data_ptr(),
+                                            k_cache.data_ptr(), v_cache.data_ptr(), slot_dev, slot_host, B * T, T, H, hd,
+                                            q.stride(1), k.stride(1), v.stride(1), k_cache.stride(0), k_cache.stride(1),
+                                            per_batch, _DTYPE_CODE[q.dtype], _stream())
+    _lib.check(rc, "rope_qk_append_")
+    launch_counter[0] += 1
+
+
 def swiglu(gate_up: torch.Tensor) -> torch.Tensor:
     """act_fn(gate) * up on a (..., 2*I) tensor holding [gate | up] (LlamaMLP, :188-189)."""
     inference_only("swiglu", gate_up)

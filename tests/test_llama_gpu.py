@@ -65,6 +65,33 @@ def test_rope_matches_reference_formula(dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("device_slot", [False, True])
+def test_rope_append_equals_rope_then_copy(dtype, device_slot):
+    """The fused RoPE + KV-cache append writes bit-for-bit what rope_qk_ followed by the two cache copies wrote."""
+    from mm_interleaved_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    B, T, H, hd, Tmax, slot = 2, (1 if device_slot else 7), 3, 128, 20, 5
+    qkv = torch.randn((B, T, 3, H, hd), generator=g).to(dtype).to(DEV)
+    pos = (torch.arange(T)[None] + torch.tensor([[slot], [slot - 2]])).to(DEV)
+    cos, sin = (t.to(DEV) for t in rotary_tables_ref(hd, 64))
+    ref = qkv.clone()
+    ops.rope_qk_(ref[:, :, 0], ref[:, :, 1], cos, sin, pos)
+    kc = torch.full((B + 1, Tmax, H, hd), 7.0, dtype=dtype, device=DEV)[:B]      # a view with a larger batch extent
+    vc = torch.full((B + 1, Tmax, H, hd), 7.0, dtype=dtype, device=DEV)[:B]
+    got = qkv.clone()
+    ops.rope_qk_append_(got[:, :, 0], got[:, :, 1], got[:, :, 2], cos, sin, pos, kc, vc,
+                        torch.tensor([slot], device=DEV) if device_slot else slot)
+    assert torch.equal(got[:, :, 0], ref[:, :, 0])                                  # q rotated in place
+    assert torch.equal(got[:, :, 1], qkv[:, :, 1]) and torch.equal(got[:, :, 2], qkv[:, :, 2])   # k, v operands untouched
+    assert torch.equal(kc[:, slot:slot + T], ref[:, :, 1]) and torch.equal(vc[:, slot:slot + T], qkv[:, :, 2])
+    for c in (kc, vc):                                                              # nothing else written
+        assert (c[:, :slot] == 7).all() and (c[:, slot + T:] == 7).all()
+    if not device_slot:
+        with pytest.raises(RuntimeError):
+            ops.rope_qk_append_(got[:, :, 0], got[:, :, 1], got[:, :, 2], cos, sin, pos, kc, vc, Tmax - T + 1)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_swiglu_matches_reference_formula(dtype):
     from mm_interleaved_b200 import ops
     g = torch.Generator().manual_seed(2)
