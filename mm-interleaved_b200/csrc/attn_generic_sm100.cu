@@ -401,6 +401,10 @@ attn_decode_split128_kernel(const T *__restrict__ q, const T *__restrict__ k, co
     orow[d] = from_op<T>(den > 0.f ? num / den : 0.f);           // fully masked row -> zeros
 }
 
+// (Tried and dropped, profiles/r02_decode_attn_staged_vs_batched.log: staging a warp's whole 64-key K and V tiles in
+// shared memory with cp.async -- 32 KB per warp requested up front, one memory round trip per CTA, 6 warps per SM --
+// ran at 62 us against 41.8 us: with so few warps the score / softmax / P V arithmetic out of shared memory is
+// latency-exposed (ncu: IPC 0.82, 8.7 % occupancy, DRAM 35 %).)
 template <typename T>
 __global__ void attn_decode_merge_kernel(const float *__restrict__ part, T *__restrict__ out, int H, int hd, int n_split,
                                          long o_bs) {
