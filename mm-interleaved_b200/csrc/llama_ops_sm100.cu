@@ -75,11 +75,14 @@ __global__ void __launch_bounds__(kRmsThreads) rmsnorm_reg_kernel(const T *__res
     const T *xr = x + row * cols;
     T *yr = y + row * cols;
     const int nvec = cols / VEC;                      // host: cols % VEC == 0, nvec <= kRmsThreads * kRmsChunks
-    uint4 v[kRmsChunks];
+    uint4 v[kRmsChunks], wv[kRmsChunks];          // the weight vectors travel with x: one memory round trip, not two
 #pragma unroll
     for (int c = 0; c < kRmsChunks; ++c) {
         const int i = threadIdx.x + c * kRmsThreads;
-        if (i < nvec) v[c] = ldg_nc_v4(xr + i * VEC);
+        if (i < nvec) {
+            v[c] = ldg_nc_v4(xr + i * VEC);
+            wv[c] = ldg_nc_v4(w + i * VEC);
+        }
     }
     float ss = 0.f;
 #pragma unroll
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(kRmsThreads) rmsnorm_reg_kernel(const T *__res
         if (i < nvec) {
             float f[VEC], g[VEC], o[VEC];
             Vec16<T>::unpack(v[c], f);
-            Vec16<T>::unpack(*reinterpret_cast<const uint4 *>(w + i * VEC), g);
+            Vec16<T>::unpack(wv[c], g);
 #pragma unroll
             for (int k = 0; k < VEC; ++k) o[k] = g[k] * rnd<T>(f[k] * r);
             stg_v4(yr + i * VEC, Vec16<T>::pack(o));
@@ -318,12 +321,14 @@ template <typename T, int ACT> __device__ __forceinline__ float glu_act(float g)
 template <typename T, int ACT = 0, bool GATE_SECOND = false>
 __global__ void __launch_bounds__(256) swiglu_kernel(const T *__restrict__ gu, T *__restrict__ out, long rows, int I) {
     // CTA per row (grid-stride): no 64-bit index division, two independent (gate, up) vector pairs in flight per thread
+    // gridDim.y > 1 (few rows, e.g. a decode step): a row is cut into column slices so that it spreads over many SMs
     constexpr int VEC = 16 / (int)sizeof(T);
-    const int nvec = I / VEC;
+    const int per = (I / VEC + gridDim.y - 1) / gridDim.y;
+    const int v0 = blockIdx.y * per, nvec = min(I / VEC, v0 + per);
     for (long r = blockIdx.x; r < rows; r += gridDim.x) {
         const T *g_row = gu + r * 2 * I + (GATE_SECOND ? I : 0), *u_row = gu + r * 2 * I + (GATE_SECOND ? 0 : I);
         T *o_row = out + r * I;
-        int i = threadIdx.x;
+        int i = v0 + threadIdx.x;
         for (; i + (int)blockDim.x < nvec; i += 2 * blockDim.x) {
             const int j = i + blockDim.x;
             const uint4 g0 = ldg_nc_v4(g_row + i * VEC), u0 = ldg_nc_v4(u_row + i * VEC);
@@ -384,7 +389,10 @@ static int launch_all(int which, const void *a, const void *b, const void *c, vo
         case 3: { // swiglu / geglu: a=gate_up d=out n0=rows i0=I i1=variant (0 silu [gate|up], 1 gelu [value|gate])
             const int nvec = i0 / (16 / (int)sizeof(T));
             const int threads = nvec >= 512 ? 256 : (nvec >= 64 ? 64 : 32);
-            const int grid = (int)(n0 < 148L * 64 ? n0 : 148L * 64);
+            const int gx = (int)(n0 < 148L * 64 ? n0 : 148L * 64);
+            int gy = 1;                                   // fewer CTAs than SMs: slice the columns (two vectors per thread)
+            if (gx < 148) { gy = (nvec + 2 * threads - 1) / (2 * threads); if (gy > 64) gy = 64; if (gy < 1) gy = 1; }
+            const dim3 grid(gx, gy);
             if (i1 == 1)
                 swiglu_kernel<T, 1, true><<<grid, threads, 0, st>>>((const T *)a, (T *)d, n0, i0);
             else

@@ -27,5 +27,5 @@ with torch.no_grad():
 rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
 tot = sum(e.device_time_total for e in rows)
 print(f"total device time {tot / 1e3:.1f} ms for prefill + {n_new + 1} tokens (batch {B}); kernels with count multiple of {n_new + 1} are per-token")
-for e in rows[:28]:
+for e in rows[:int(os.environ.get('TOP', 45))]:
     print(f"{e.device_time_total / 1e3:9.2f} ms  n={e.count:5d}  avg={e.device_time_total / max(e.count, 1):8.1f} us  {e.key[:100]}")
