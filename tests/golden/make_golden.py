@@ -234,6 +234,34 @@ def make_llama(ref_ns):
     print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+LLAMA_TC = dict(B=2, T=200, n_img=3, seed=123, left_pad=5)      # > 128 rows: two query tiles, four 64-key tiles, padding
+
+
+def make_llama_tc(ref_ns):
+    """The same tiny reference LlamaModel (head_dim 128) on a 200-token prompt: long enough that this repo's 16-bit run
+    takes the tcgen05 attention kernel (>= 16 query rows) in every layer, jointly with the fused MMFS sampler.  The
+    golden is the reference's fp32 output; the GPU test runs fp16 / bf16 against it (tests/test_llama_gpu.py)."""
+    from transformers import LlamaConfig
+    cfg = LlamaConfig(**{k: v for k, v in LLAMA_TINY.items() if k not in ("cross_attention_frequency", "spatial_shapes", "image_embed_dim")},
+                      hidden_act="silu")
+    cfg.max_position_embeddings = 256
+    cfg.cross_attention_frequency = LLAMA_TINY["cross_attention_frequency"]
+    cfg.spatial_shapes = LLAMA_TINY["spatial_shapes"]
+    cfg.image_embed_dim = LLAMA_TINY["image_embed_dim"]
+    model = ref_ns.llama.LlamaModel(cfg).eval()
+    sd = seeded_state_dict(model.state_dict(), seed=4242)
+    model.load_state_dict(sd)
+    c = LLAMA_TC
+    embeds, vision, attn_mask, position_ids, cross = llama_inputs(LLAMA_TINY, c["B"], c["T"], c["n_img"], seed=c["seed"], left_pad=c["left_pad"])
+    with torch.no_grad():
+        out = model(inputs_embeds=embeds, attention_mask=attn_mask, position_ids=position_ids,
+                    vision_hidden_states=vision, cross_attention_mask=cross, use_cache=False, return_dict=True)
+    path = os.path.join(HERE, "llama_tc.npz")
+    np.savez_compressed(path, prefill_fp32=out.last_hidden_state.numpy().astype(np.float32),
+                        weight_checksum=np.array(float(sum(v.double().sum() for v in sd.values()))))
+    print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 # ---------------------------------------------------------------------------------------------
 # MMFSNet (decoders/sd_mmfs.py) -- tiny UNet skeleton: 2 resolution stages, 4 skip tensors + mid
 # ---------------------------------------------------------------------------------------------
@@ -494,6 +522,7 @@ if __name__ == "__main__":
         make_mmfsnet(ref_loader.load())
     if "llama" in which:
         make_llama(ref_loader.load())
+        make_llama_tc(ref_loader.load())
     if "msda" in which:
         main()
     if "mmfs" in which:

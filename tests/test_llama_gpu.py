@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 from oracle import error_metrics  # noqa: E402
 from oracle.llama import additive_mask_ref, rotary_tables_ref  # noqa: E402
 from oracle.mmfs import rms_norm_ref  # noqa: E402
-from tests.golden.make_golden import LLAMA_TINY, llama_inputs  # noqa: E402
+from tests.golden.make_golden import LLAMA_TC, LLAMA_TINY, llama_inputs, seeded_state_dict  # noqa: E402
 from tests.test_oracle_llama import tiny_state_dict  # noqa: E402
 
 DEV = "cuda"
@@ -165,6 +165,52 @@ def test_model_bf16_tracks_fp32_reference():
     valid = attn_mask.bool()
     err = (out.last_hidden_state.float().cpu() - ref).abs()[valid]
     assert err.max() <= 6e-2 * ref[valid].abs().max()      # bf16 storage through 3 layers
+
+
+@pytest.mark.parametrize("dtype,max_tol,rms_tol", [(torch.float16, 3.0e-3, 2.5e-3), (torch.bfloat16, 2.5e-2, 2.0e-2),
+                                                   (torch.float32, 1.0e-5, 1.0e-5)])
+def test_long_prompt_takes_the_tcgen05_kernel_and_tracks_the_reference_golden(dtype, max_tol, rms_tol):
+    """A 200-token left-padded prompt through the tiny decoder in 16 bit: every layer's self-attention goes through the
+    tcgen05 kernel (two query tiles, four key tiles, padding mask, causal diagonal) and every second layer through the
+    fused MMFS sampler -- jointly against the fp32 output of the REFERENCE LlamaModel on the same weights and inputs
+    (tests/golden/llama_tc.npz, generated by make_golden.make_llama_tc from the reference's own modeling file).
+    Tolerances are for 16-bit storage through 3 layers: max error relative to max |ref|, and relative RMS error (measured
+    on a B200: fp16 1.5e-3 / 1.2e-3, bf16 1.1e-2 / 9.6e-3).  fp32 takes the bandwidth kernel (the tensor-core kernel is
+    16-bit only) and must match to 1e-5 (measured 7e-7)."""
+    import os
+
+    import numpy as np
+    from mm_interleaved_b200 import attn_tc
+    from mm_interleaved_b200.llama_mmfs import LlamaMMFSConfig, LlamaModel
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "llama_tc.npz"))
+    model = LlamaModel(LlamaMMFSConfig(**{**LLAMA_TINY, "max_position_embeddings": 256}))
+    sd = seeded_state_dict(model.state_dict(), seed=4242)
+    assert abs(float(sum(v.double().sum() for v in sd.values())) - float(z["weight_checksum"])) < 1e-6
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV, dtype).eval()
+    c = LLAMA_TC
+    embeds, vision, attn_mask, position_ids, cross = llama_inputs(LLAMA_TINY, c["B"], c["T"], c["n_img"], seed=c["seed"], left_pad=c["left_pad"])
+    calls, real = [], attn_tc.forward
+
+    def spy(*a, **k):
+        calls.append(1)
+        return real(*a, **k)
+
+    attn_tc.forward = spy
+    try:
+        with torch.no_grad():
+            out = model(inputs_embeds=embeds.to(DEV, dtype), attention_mask=attn_mask.to(DEV), position_ids=position_ids.to(DEV),
+                        vision_hidden_states=vision.to(DEV, dtype), cross_attention_mask=cross.to(DEV), use_cache=False)
+    finally:
+        attn_tc.forward = real
+    assert len(calls) == (0 if dtype == torch.float32 else LLAMA_TINY["num_hidden_layers"])   # tensor-core kernel in every layer
+    ref = torch.from_numpy(z["prefill_fp32"])
+    valid = attn_mask.bool()
+    got = out.last_hidden_state.float().cpu()
+    err = (got - ref)[valid]
+    assert torch.isfinite(got[valid]).all()
+    assert err.abs().max() <= max_tol * ref[valid].abs().max(), float(err.abs().max() / ref[valid].abs().max())
+    assert err.pow(2).mean().sqrt() <= rms_tol * ref[valid].pow(2).mean().sqrt(), float(err.pow(2).mean().sqrt() / ref[valid].pow(2).mean().sqrt())
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
