@@ -253,6 +253,15 @@ int mmfs_attn_forward(const void *q, const void *k, const void *v, void *out, co
                       long q_bs, long q_ts, long k_bs, long k_ts, long v_bs, long v_ts, long o_bs, long o_ts,
                       float scale, int causal, int past, int dtype, void *stream);
 
+/* The same op as a PERSISTENT kernel: 2 CTAs per SM walk the (batch, query tile, head) items handed out by an atomic
+ * counter, with barriers / TMEM / tensor maps set up once and the next item's loads and first MMA overlapping the
+ * current item's O read-out.  Taken when there are more items than resident CTAs (else the call runs the kernel above).
+ * work_counter: one device uint32 that is ZERO when the kernel starts and private to the call until it completes. */
+int mmfs_attn_forward_persistent(const void *q, const void *k, const void *v, void *out, const uint8_t *key_mask,
+                                 int B, int H, int Tq, int Tkv, int hd,
+                                 long q_bs, long q_ts, long k_bs, long k_ts, long v_bs, long v_ts, long o_bs, long o_ts,
+                                 float scale, int causal, int past, int dtype, unsigned *work_counter, void *stream);
+
 /*
  * 2-D convolution as an implicit GEMM on the tensor cores (tcgen05, TMA-shifted input boxes, no im2col buffer).
  * Replaces the cuDNN convolutions diffusers' UNet issues in the denoise step (called from

@@ -309,6 +309,299 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Persistent variant.  A sweep over sequence lengths (tools/attn_sweep.py, 2560 CTAs each time) fits the kernel above
+// to  t_CTA = 12 us + 0.9 us x key tiles  of CTA slot time: launch, barrier init, TMEM allocation, the Q / K0 / V0 load
+// round trip, the pipeline fill of the first tile and the O read-out are paid per (query tile, head, batch) item and
+// are NOT hidden by the second resident CTA, because one CTA alone is softmax-latency bound -- at the cfg-3 prefill
+// (17 key tiles per item on average) that is ~40 % of the run.  Here 2 CTAs per SM stay resident and walk a work list:
+//   * items (batch-major, longest query tile first, heads fastest -- the order of the grid above) are handed out by an
+//     atomic counter (list scheduling: 1.01-1.04x the ideal makespan; a static round robin is 1.14-1.19x);
+//   * barriers, TMEM and the tensor maps are set up once; every per-tile barrier runs on a GLOBAL tile counter, so the
+//     K / V ring and the S / P ping-pong continue across items without a drain;
+//   * the producer requests the next item's Q (after `q_empty`: the last S MMA of the current item retired), K0, V0
+//     while the current item's last softmax, P V and O read-out run; the MMA thread issues the next item's first S
+//     MMA under the O read-out and waits for `o_free` only before it overwrites O.
+template <typename T, int HD>
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                           const __grid_constant__ CUtensorMap map_v, const AttnParams p, unsigned *__restrict__ sched, int n_work) {
+    constexpr int NBOX = HD / 64;
+    constexpr uint32_t QBOX_BYTES = kBM * 128, KBOX_BYTES = kBN * 128;
+    constexpr uint32_t Q_BYTES = NBOX * QBOX_BYTES, KV_BYTES = NBOX * KBOX_BYTES;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if ((s_addr(smem_raw) & 1023u) != 0u) { asm volatile("trap;"); }
+    uint8_t *sQ = smem_raw;
+    uint8_t *sK = sQ + Q_BYTES;
+    uint8_t *sV = sK + 2 * KV_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sV + 2 * KV_BYTES);
+    uint64_t *q_full = bars + 0, *k_full = bars + 1 /*[2]*/, *v_full = bars + 3 /*[2]*/, *k_empty = bars + 5 /*[2]*/,
+             *v_empty = bars + 7 /*[2]*/, *s_full = bars + 9 /*[2]*/, *p_full = bars + 11, *o_ready = bars + 12,
+             *q_empty = bars + 13, *o_free = bars + 14, *item_full = bars + 15 /*[2]*/, *item_empty = bars + 17 /*[2]*/;
+    uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + 19);
+    int *s_item = reinterpret_cast<int *>(bars + 19) + 2;         // [2]
+    float *s_kadd = reinterpret_cast<float *>(bars + 22);        // [2][64], 16-byte aligned
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_q = (p.Tq + kBM - 1) / kBM;
+    // item w -> (batch, query tile, head): batch-major, longest tile first inside a batch entry, heads fastest
+    auto decode = [&](int w, int &m_tile, int &h, int &b, int &q0, int &n_tiles) {
+        b = w / (n_q * p.H);
+        const int r = w - b * (n_q * p.H);
+        const int mi = r / p.H;
+        h = r - mi * p.H;
+        m_tile = p.causal ? n_q - 1 - mi : mi;
+        q0 = m_tile * kBM;
+        int kv_end = p.Tkv;
+        if (p.causal) kv_end = min(p.Tkv, p.past + min(q0 + kBM, p.Tq));
+        n_tiles = (kv_end + kBN - 1) / kBN;
+    };
+
+    if (threadIdx.x == 0) {
+        bar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            bar_init(k_full + i, 1); bar_init(v_full + i, 1); bar_init(k_empty + i, 1); bar_init(v_empty + i, 1); bar_init(s_full + i, 1);
+            bar_init(item_full + i, 1); bar_init(item_empty + i, 129);          // MMA thread + 128 softmax threads
+        }
+        bar_init(p_full, 128);
+        bar_init(o_ready, 1);
+        bar_init(q_empty, 1);
+        bar_init(o_free, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(tmem_base_smem)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+    const uint32_t tmem_s0 = tmem_base, tmem_o = tmem_base + 2 * kBN;
+
+    if (warp == 0) {
+        // ============================== scheduler + TMA producer ==============================
+        if (lane == 0) {
+            int w = blockIdx.x;                                      // the first item is static (grid <= n_work)
+            int g = 0;                                               // global tile counter
+            for (int qn = 0;; ++qn) {
+                const int slot = qn & 1;
+                if (qn >= 2) bar_wait(item_empty + slot, ((qn >> 1) - 1) & 1);
+                s_item[slot] = w < n_work ? w : -1;
+                bar_arrive(item_full + slot);
+                if (w >= n_work) break;
+                const int w_next = (int)gridDim.x + (int)atomicAdd(sched, 1u);   // fetched early: the latency hides under this item
+                int m_tile, h, b, q0, n_tiles;
+                decode(w, m_tile, h, b, q0, n_tiles);
+                if (qn > 0) bar_wait(q_empty, (qn - 1) & 1);        // the previous item's S MMAs no longer read Q
+                bar_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+                for (int bx = 0; bx < NBOX; ++bx) tma_load_4d(sQ + bx * QBOX_BYTES, &map_q, q_full, bx * 64, h, q0, b);
+                for (int j = 0; j < n_tiles; ++j, ++g) {
+                    const int s = g & 1;
+                    const uint32_t ph = (g >> 1) & 1;
+                    bar_wait(k_empty + s, ph ^ 1);
+                    bar_expect_tx(k_full + s, KV_BYTES);
+#pragma unroll
+                    for (int bx = 0; bx < NBOX; ++bx)
+                        tma_load_4d(sK + s * KV_BYTES + bx * KBOX_BYTES, &map_k, k_full + s, bx * 64, h, j * kBN, b);
+                    bar_wait(v_empty + s, ph ^ 1);
+                    bar_expect_tx(v_full + s, KV_BYTES);
+#pragma unroll
+                    for (int bx = 0; bx < NBOX; ++bx)
+                        tma_load_4d(sV + s * KV_BYTES + bx * KBOX_BYTES, &map_v, v_full + s, bx * 64, h, j * kBN, b);
+                }
+                w = w_next;
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer (one thread) ==============================
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = instr_desc(AttnFmt<T>::code, 0, kBM, kBN);
+            constexpr uint32_t idesc_o = instr_desc(AttnFmt<T>::code, 1, kBM, HD);
+            auto issue_s = [&](int g) {
+                const int s = g & 1;
+                bar_wait(k_full + s, (g >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < HD / 16; ++kk)
+                    umma_f16(tmem_s0 + (uint32_t)s * kBN,
+                             smem_desc(s_addr(sQ) + (kk >> 2) * QBOX_BYTES + (kk & 3) * 32, 16, 1024),
+                             smem_desc(s_addr(sK) + s * KV_BYTES + (kk >> 2) * KBOX_BYTES + (kk & 3) * 32, 16, 1024),
+                             idesc_s, kk > 0);
+                umma_commit(s_full + s);
+                umma_commit(k_empty + s);
+            };
+            int g = 0;
+            for (int qn = 0;; ++qn) {
+                const int slot = qn & 1;
+                bar_wait(item_full + slot, (qn >> 1) & 1);
+                const int w = s_item[slot];
+                bar_arrive(item_empty + slot);
+                if (w < 0) break;
+                int m_tile, h, b, q0, n_tiles;
+                decode(w, m_tile, h, b, q0, n_tiles);
+                bar_wait(q_full, qn & 1);
+                if (n_tiles > 0) issue_s(g);
+                if (n_tiles <= 1) umma_commit(q_empty);             // Q is free once the item's last S MMA retires
+                for (int j = 0; j < n_tiles; ++j, ++g) {
+                    if (j + 1 < n_tiles) {
+                        issue_s(g + 1);                              // overlaps with the softmax of tile j
+                        if (j + 2 == n_tiles) umma_commit(q_empty);
+                    }
+                    const int s = g & 1;
+                    bar_wait(p_full, g & 1);
+                    bar_wait(v_full + s, (g >> 1) & 1);
+                    if (j == 0 && qn > 0) bar_wait(o_free, (qn - 1) & 1);   // the previous item's O has been read out
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < kBN / 16; ++kk)
+                        umma_f16_ts(tmem_o, tmem_s0 + (uint32_t)s * kBN + kk * 8,
+                                    smem_desc(s_addr(sV) + s * KV_BYTES + kk * 16 * 128, KBOX_BYTES, 1024), idesc_o, (j > 0) || (kk > 0));
+                    umma_commit(o_ready);
+                    umma_commit(v_empty + s);
+                }
+            }
+        }
+    } else {
+        // ============================== softmax / correction / epilogue ==============================
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int tid = threadIdx.x - 64;
+        const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+        int g = 0;
+        for (int qn = 0;; ++qn) {
+            const int slot = qn & 1;
+            bar_wait(item_full + slot, (qn >> 1) & 1);
+            const int w = s_item[slot];
+            bar_arrive(item_empty + slot);
+            if (w < 0) break;
+            int m_tile, h, b, q0, n_tiles;
+            decode(w, m_tile, h, b, q0, n_tiles);
+            const int q_abs = q0 + row;
+            float m_ref = -INFINITY, l_run = 0.f;
+            const int causal_limit = p.causal ? (p.past + q_abs) : 0x7fffffff;
+            const int warp_causal_limit = p.causal ? (p.past + q0 + quarter * 32) : 0x7fffffff;
+
+            for (int j = 0; j < n_tiles; ++j, ++g) {
+                const int s = g & 1;
+                const int k0 = j * kBN;
+                if (p.key_mask != nullptr) {
+                    if (tid < kBN) {
+                        const int kj = k0 + tid;
+                        s_kadd[s * kBN + tid] = (kj < p.Tkv && p.key_mask[(long)b * p.Tkv + kj]) ? 0.f : -INFINITY;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                bar_wait(s_full + s, (g >> 1) & 1);
+                tc_fence_after();
+                const bool need_mask = (k0 + kBN - 1 > warp_causal_limit) || (k0 + kBN > p.Tkv) || (p.key_mask != nullptr);
+                float sc[kBN];
+                tmem_ld64(tmem_s0 + (uint32_t)s * kBN + lane_sel, sc);
+                if (need_mask) {
+                    if (p.key_mask != nullptr) {
+                        const float4 *ka = reinterpret_cast<const float4 *>(s_kadd + s * kBN);
+#pragma unroll
+                        for (int i = 0; i < kBN; i += 4) {
+                            const float4 a = ka[i >> 2];
+                            unpack_f32x2(add_f32x2(pack_f32x2(sc[i], sc[i + 1]), pack_f32x2(a.x, a.y)), sc[i], sc[i + 1]);
+                            unpack_f32x2(add_f32x2(pack_f32x2(sc[i + 2], sc[i + 3]), pack_f32x2(a.z, a.w)), sc[i + 2], sc[i + 3]);
+                        }
+                    }
+                    const int cnt = min(p.Tkv - k0, p.causal ? causal_limit - k0 + 1 : kBN);
+#pragma unroll
+                    for (int i = 0; i < kBN; ++i) sc[i] = (i < cnt) ? sc[i] : -INFINITY;
+                }
+                float m_tile_max = fmaxf(sc[0], sc[1]);
+#pragma unroll
+                for (int i = 2; i < kBN; i += 2) m_tile_max = fmaxf(m_tile_max, fmaxf(sc[i], sc[i + 1]));
+                const float m_cand = fmaxf(m_ref, m_tile_max);
+                const bool grow = (m_cand > m_ref) && (m_ref == -INFINITY || (m_cand - m_ref) * p.scale_log2e > kRescaleThreshold);
+                const float alpha = grow ? ((m_ref == -INFINITY) ? 0.f : fast_exp2((m_ref - m_cand) * p.scale_log2e)) : 1.f;
+                if (grow) m_ref = m_cand;
+                const float m_scaled = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2e;
+                const uint64_t sc2 = pack_f32x2(p.scale_log2e, p.scale_log2e), neg_m2 = pack_f32x2(-m_scaled, -m_scaled);
+                uint64_t l2a = 0ull, l2b = 0ull;
+                uint32_t pk[kBN / 2];
+#pragma unroll
+                for (int i = 0; i < kBN; i += 4) {
+                    float x0, x1, x2, x3;
+                    unpack_f32x2(fma_f32x2(pack_f32x2(sc[i], sc[i + 1]), sc2, neg_m2), x0, x1);
+                    unpack_f32x2(fma_f32x2(pack_f32x2(sc[i + 2], sc[i + 3]), sc2, neg_m2), x2, x3);
+                    const float e0 = fast_exp2(x0), e1 = fast_exp2(x1), e2 = fast_exp2(x2), e3 = fast_exp2(x3);
+                    l2a = add_f32x2(l2a, pack_f32x2(e0, e1));
+                    l2b = add_f32x2(l2b, pack_f32x2(e2, e3));
+                    pk[i >> 1] = pack2<T>(e0, e1);
+                    pk[(i >> 1) + 1] = pack2<T>(e2, e3);
+                }
+                float la, lb, lc, ld;
+                unpack_f32x2(l2a, la, lb);
+                unpack_f32x2(l2b, lc, ld);
+                l_run = l_run * alpha + ((la + lb) + (lc + ld));
+
+                const bool any_grow = __any_sync(0xffffffffu, grow) && (j > 0);
+                if (any_grow) {
+                    bar_wait(o_ready, (g - 1) & 1);
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int c = 0; c < HD; c += 32) {
+                        float o[32];
+                        tmem_ld32(tmem_o + lane_sel + c, o);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] *= alpha;
+                        tmem_st32(tmem_o + lane_sel + c, o);
+                    }
+                }
+                tmem_st32_u32(tmem_s0 + (uint32_t)s * kBN + lane_sel, pk);
+                if (j > 0 && !any_grow) bar_wait(o_ready, (g - 1) & 1);   // protocol guard (see the kernel above)
+                tc_fence_before();
+                bar_arrive(p_full);
+            }
+
+            // epilogue: O / l -> global; O is released to the next item as soon as its last columns are in registers
+            if (n_tiles > 0) {
+                bar_wait(o_ready, (g - 1) & 1);
+                tc_fence_after();
+            }
+            const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
+            T *op = static_cast<T *>(p.out) + (long)b * p.o_bs + (long)q_abs * p.o_ts + (long)h * HD;
+#pragma unroll 1
+            for (int c = 0; c < HD; c += 32) {
+                float o[32];
+                if (n_tiles > 0) {
+                    tmem_ld32(tmem_o + lane_sel + c, o);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = 0.f;
+                }
+                if (c + 32 == HD) {
+                    tc_fence_before();
+                    bar_arrive(o_free);
+                }
+                if (q_abs < p.Tq) {
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        uint4 wv;
+                        wv.x = pack2<T>(o[qd * 8 + 0] * inv, o[qd * 8 + 1] * inv);
+                        wv.y = pack2<T>(o[qd * 8 + 2] * inv, o[qd * 8 + 3] * inv);
+                        wv.z = pack2<T>(o[qd * 8 + 4] * inv, o[qd * 8 + 5] * inv);
+                        wv.w = pack2<T>(o[qd * 8 + 6] * inv, o[qd * 8 + 7] * inv);
+                        *reinterpret_cast<uint4 *>(op + c + qd * 8) = wv;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 // (B, T, H, hd) tensor with element strides bs / ts (heads dense): dims innermost-first {hd, H, T, B}
 // Encoding a tensor map costs a driver call (~1-2 us on the host, three per launch); the decoder calls this op
@@ -356,16 +649,31 @@ static int make_map_uncached(CUtensorMap *map, const void *ptr, int dtype, int B
 }
 
 template <typename T, int HD>
-static int launch_attn(const CUtensorMap &mq, const CUtensorMap &mk, const CUtensorMap &mv, const AttnParams &p, cudaStream_t st) {
+static int launch_attn(const CUtensorMap &mq, const CUtensorMap &mk, const CUtensorMap &mv, const AttnParams &p, unsigned *sched,
+                       cudaStream_t st) {
+    const int dev = current_device();
+    const int n_q = (p.Tq + kBM - 1) / kBM;
+    const long n_work = (long)n_q * p.H * p.B;
+    if (sched != nullptr && n_work > 2L * num_sms() && n_work < (1L << 30)) {     // more items than resident CTAs: persistent
+        constexpr size_t smem = (size_t)(HD / 64) * (kBM * 128 + 4 * kBN * 128) + 22 * 8 + 2 * kBN * sizeof(float) + 16;
+        auto kern = attn_fwd_persistent_kernel<T, HD>;
+        static bool attr_set[kMaxDevices] = {};
+        if (dev < 0 || dev >= kMaxDevices || !attr_set[dev]) {
+            MMFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < kMaxDevices) attr_set[dev] = true;
+        }
+        kern<<<2 * num_sms(), kAttnThreads, smem, st>>>(mq, mk, mv, p, sched, (int)n_work);
+        MMFS_CUDA(cudaGetLastError());
+        return MMFS_OK;
+    }
     constexpr size_t smem = (size_t)(HD / 64) * (kBM * 128 + 4 * kBN * 128) + 14 * 8 + 2 * kBN * sizeof(float) + 16;
     auto kern = attn_fwd_kernel<T, HD>;
     static bool attr_set[kMaxDevices] = {};          // the attribute is per device
-    const int dev = current_device();
     if (dev < 0 || dev >= kMaxDevices || !attr_set[dev]) {
         MMFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < kMaxDevices) attr_set[dev] = true;
     }
-    dim3 grid(p.H, (p.Tq + kBM - 1) / kBM, p.B);
+    dim3 grid(p.H, n_q, p.B);
     kern<<<grid, kAttnThreads, smem, st>>>(mq, mk, mv, p);
     MMFS_CUDA(cudaGetLastError());
     return MMFS_OK;
@@ -375,10 +683,10 @@ static int launch_attn(const CUtensorMap &mq, const CUtensorMap &mk, const CUten
 
 using namespace mmfs;
 
-extern "C" int mmfs_attn_forward(const void *q, const void *k, const void *v, void *out, const uint8_t *key_mask,
-                                 int B, int H, int Tq, int Tkv, int hd,
-                                 long q_bs, long q_ts, long k_bs, long k_ts, long v_bs, long v_ts, long o_bs, long o_ts,
-                                 float scale, int causal, int past, int dtype, void *stream) {
+static int attn_forward_impl(const void *q, const void *k, const void *v, void *out, const uint8_t *key_mask,
+                             int B, int H, int Tq, int Tkv, int hd,
+                             long q_bs, long q_ts, long k_bs, long k_ts, long v_bs, long v_ts, long o_bs, long o_ts,
+                             float scale, int causal, int past, int dtype, unsigned *sched, void *stream) {
     MMFS_CHECK_ARG(B >= 0 && H > 0 && Tq >= 0 && Tkv > 0, "attn_forward: bad shape");
     if (B == 0 || Tq == 0) return MMFS_OK;
     MMFS_CHECK_ARG(q && k && v && out, "attn_forward: null pointer argument");
@@ -405,6 +713,24 @@ extern "C" int mmfs_attn_forward(const void *q, const void *k, const void *v, vo
     p.debug = debug;
 #endif
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == MMFS_BF16) return hd == 64 ? launch_attn<__nv_bfloat16, 64>(mq, mk, mv, p, st) : launch_attn<__nv_bfloat16, 128>(mq, mk, mv, p, st);
-    return hd == 64 ? launch_attn<__half, 64>(mq, mk, mv, p, st) : launch_attn<__half, 128>(mq, mk, mv, p, st);
+    if (dtype == MMFS_BF16)
+        return hd == 64 ? launch_attn<__nv_bfloat16, 64>(mq, mk, mv, p, sched, st) : launch_attn<__nv_bfloat16, 128>(mq, mk, mv, p, sched, st);
+    return hd == 64 ? launch_attn<__half, 64>(mq, mk, mv, p, sched, st) : launch_attn<__half, 128>(mq, mk, mv, p, sched, st);
+}
+
+extern "C" int mmfs_attn_forward(const void *q, const void *k, const void *v, void *out, const uint8_t *key_mask,
+                                 int B, int H, int Tq, int Tkv, int hd,
+                                 long q_bs, long q_ts, long k_bs, long k_ts, long v_bs, long v_ts, long o_bs, long o_ts,
+                                 float scale, int causal, int past, int dtype, void *stream) {
+    return attn_forward_impl(q, k, v, out, key_mask, B, H, Tq, Tkv, hd, q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, o_bs, o_ts, scale, causal,
+                             past, dtype, nullptr, stream);
+}
+
+extern "C" int mmfs_attn_forward_persistent(const void *q, const void *k, const void *v, void *out, const uint8_t *key_mask,
+                                            int B, int H, int Tq, int Tkv, int hd,
+                                            long q_bs, long q_ts, long k_bs, long k_ts, long v_bs, long v_ts, long o_bs, long o_ts,
+                                            float scale, int causal, int past, int dtype, unsigned *work_counter, void *stream) {
+    MMFS_CHECK_ARG(work_counter != nullptr && (uintptr_t)work_counter % 4 == 0, "attn_forward_persistent: work_counter must be a zeroed device uint32");
+    return attn_forward_impl(q, k, v, out, key_mask, B, H, Tq, Tkv, hd, q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, o_bs, o_ts, scale, causal,
+                             past, dtype, work_counter, stream);
 }

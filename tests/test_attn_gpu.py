@@ -4,7 +4,7 @@ softmax(q k^T / sqrt(d) + mask) v on the same bf16/f16-rounded inputs.
 Tolerance, elementwise: P is rounded to the 16-bit type before the second MMA (as in the reference, where
 `attn_weights.to(query_states.dtype)` precedes the PV matmul, decoders/modeling_llama_mmfs.py:261-262), so with u the
 unit roundoff of the type (2^-9 bf16, 2^-12 f16) every probability carries a relative error <= u and the output one more
-rounding:  |err| <= 2.5 u (P |V|) + u |ref|  (2.5: rounding of p + ex2.approx + the fp32 row sum), evaluated with the
+rounding:  |err| <= 3 u (P |V|) + u |ref|  (3: rounding of p, ex2.approx, the fp32 row sum and the lazy rescale), evaluated with the
 fp32 statement.  Kept beside it: the coarse per-tensor bounds |err| <= 2e-2 max|ref|, mean |err| <= 2e-3 max|ref|."""
 import pytest
 import torch
@@ -43,6 +43,9 @@ CASES = [
     (2, 2, 640, 640, 128, True, 0, True),       # five query tiles, padding mask
     (1, 3, 1000, 1000, 64, False, 0, False),    # ragged tails of the last query tile and of the key tiles
     (1, 2, 384, 900, 128, True, 516, True),     # chunked prefill on a cache
+    (3, 40, 640, 640, 128, True, 0, True),      # 600 items > 296 resident CTAs: the persistent work-list kernel, masks
+    (2, 24, 1000, 1000, 64, False, 0, False),   # persistent, hd 64, ragged tails
+    (40, 10, 130, 130, 128, True, 0, False),    # persistent, two-tile items incl. a 2-row query tile
 ]
 
 
@@ -70,7 +73,7 @@ def test_tc_attention_matches_eager(case, dtype):
     scale = ref.abs().max()
     assert torch.isfinite(out.float()).all()
     u = 2.0 ** -9 if dtype == torch.bfloat16 else 2.0 ** -12
-    bound = 2.5 * u * pv_abs + u * ref.abs() + 1e-6
+    bound = 3.0 * u * pv_abs + u * ref.abs() + 1e-6
     assert (err <= bound).all(), float((err / bound).max())
     assert err.max() <= 2e-2 * scale, (err.max().item(), scale.item())
     assert err.mean() <= 2e-3 * scale
