@@ -236,6 +236,8 @@ int mmfs_attn_generic(const void *q, const void *k, const void *v, void *out, co
  * private to the call until it completes (per-(b, h) arrival tickets, zeroed by the call itself on `stream`, + partials).
  * causal != 0: the query sits at position `past` and sees keys 0..past.  f32 / f16 / bf16, hd % 32 == 0, hd <= 256. */
 long mmfs_attn_decode_scratch_floats(int B, int H, int Tkv, int hd);
+/* measurement hook: warps per 256-key CTA of the hd-128 16-bit decode kernel: 4 (64 keys per warp, default) or 8 (32) */
+int mmfs_attn_decode_set_tuning(int warps);
 int mmfs_attn_decode(const void *q, const void *k, const void *v, void *out, const uint8_t *key_mask, float *scratch,
                      int B, int H, int Tkv, int hd, long q_bs, long k_bs, long k_ts, long v_bs, long v_ts, long o_bs,
                      float scale, int causal, int past, int dtype, void *stream);

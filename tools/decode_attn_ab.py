@@ -39,6 +39,10 @@ def bench(q, ks, vs, reps=20):
     return ts[len(ts) // 2], ts[0]
 
 
+from mm_interleaved_b200 import _lib  # noqa: E402
+W = int(os.environ.get("DEC_WARPS", 0))
+assert _lib.lib().mmfs_attn_decode_set_tuning(W) == 0
+print(f"decode attention: {W or 4} warps per 256-key CTA")
 nbytes = 2 * B * T * H * hd * 2
 for name, shape, qshape in (("B,T,H,hd", (B, T, H, hd), (B, 1, H, hd)), ("B*H,T,1,hd", (B * H, T, 1, hd), (B * H, 1, 1, hd))):
     ks = [torch.randn(shape, device="cuda", dtype=torch.bfloat16, generator=g) for _ in range(3)]   # 3 x 170 MB > L2
