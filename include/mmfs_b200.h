@@ -216,6 +216,10 @@ int mmfs_geglu(const void *value_gate, void *out, long rows, int inter, int dtyp
  * call leaves them zero again (arrival tickets of the split between SMs + fp32 partial tiles), so one zeroed buffer of
  * the largest N serves every call made on one stream.  MMFS_EUNSUPPORTED for shapes outside these limits. */
 long mmfs_linear_skinny_scratch_floats(int N);
+/* measurement hooks: mode 0 = default (tensor-map TMA kernel when N % 128 == 0), 1 = per-lane cp.async kernel, 2 = TMA
+ * kernel, + 4 = record per-CTA {entry, first stage, last stage, exit} globaltimer stamps, read back by ..._probe */
+int mmfs_linear_skinny_set_tuning(int mode);
+int mmfs_linear_skinny_probe(unsigned long long *host_out, int n_ctas);
 int mmfs_linear_skinny(const void *x, const void *w, void *y, const void *residual, const void *norm_weight, float *scratch,
                        int M, int N, int K, int prologue, float eps, int dtype, void *stream);
 

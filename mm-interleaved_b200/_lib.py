@@ -44,6 +44,8 @@ SIGNATURES = {
     "mmfs_swiglu": (_I, [_P, _P, _L, _I, _I, _P]),
     "mmfs_geglu": (_I, [_P, _P, _L, _I, _I, _P]),
     "mmfs_linear_skinny_scratch_floats": (_L, [_I]),
+    "mmfs_linear_skinny_set_tuning": (_I, [_I]),
+    "mmfs_linear_skinny_probe": (_I, [_P, _I]),
     "mmfs_linear_skinny": (_I, [_P] * 6 + [_I] * 4 + [_F, _I, _P]),
     "mmfs_attn_generic": (_I, [_P] * 5 + [_I] * 5 + [_L] * 8 + [_F, _I, _I, _I, _P]),
     "mmfs_groupnorm_nhwc": (_I, [_P] * 5 + [_I] * 4 + [_F, _I, _I, _P]),

@@ -37,7 +37,7 @@
 //     in caller-provided scratch that must be ZERO before the first call and is left zero by every call (no memset
 //     node per linear in the decode graph); calls sharing a scratch buffer must be ordered (one stream).
 // Roofline: HBM, N * K * sizeof(T) bytes per call.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace mmfs {
 
@@ -63,6 +63,7 @@ struct SkinnyArgs {
     float eps;
     int spb, total, q, rm;                                // steps per block (K / 512), total steps, steps per CTA (q, +1 for c < rm)
     int xp;                                               // bytes between x rows in shared memory
+    unsigned long long *dbg;                              // timing probe (tools/skinny_timeline.py): 4 globaltimer stamps per CTA, or null
 };
 
 template <typename T> struct SkMma;
@@ -105,27 +106,55 @@ __device__ __forceinline__ int sk_cta_of(int f, int q, int rm) {          // the
 __device__ __forceinline__ uint4 sk_perm(const uint4 &v) { return make_uint4(v.x, v.z, v.y, v.w); }
 
 // ---- x -> shared memory through the prologue (all 512 threads) ----------------------------------------------------------
-template <typename T>
+// All global loads of a pass are issued in batches of kSkXBatch independent vectors per thread BEFORE anything is done
+// with them: the first version walked the rows with load -> use -> load and cost 8-15 us per call (x sits in L2, ~0.4 us
+// per dependent round trip, up to 32 of them for the 13824-wide SwiGLU operand) -- the whole gap to the library kernels.
+constexpr int kSkXBatch = 8;
+
+template <typename T, int NT, bool PERM>
 __device__ __forceinline__ void sk_stage_x(const SkinnyArgs &a, uint8_t *xs, float *s_red, int tid) {
     constexpr int VEC = 8;
-    const int nvec = a.K / VEC;                                          // 16-byte vectors per row
+    auto put = [&](uint8_t *dst, const uint4 &v) { *reinterpret_cast<uint4 *>(dst) = PERM ? sk_perm(v) : v; };
+    auto sync_all = [&]() {
+        if (NT == kSkThreads) __syncthreads();
+        else asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+    };
+    const int nvec = a.K / VEC;                                          // 16-byte vectors per operand row
+    const int total = a.M * nvec;
     const T *x = static_cast<const T *>(a.x);
-    if (a.prologue == 0) {
-        for (int m = 0; m < a.M; ++m)
-            for (int j = tid; j < nvec; j += kSkThreads)
-                *reinterpret_cast<uint4 *>(xs + (size_t)m * a.xp + j * 16) = sk_perm(ldg_nc_v4(x + (size_t)m * a.K + j * VEC));
+    if (a.prologue == 0) {                                               // x is [M][K] contiguous: vector i sits at x + 8 i
+        for (int i0 = tid; i0 < total; i0 += NT * kSkXBatch) {
+            uint4 v[kSkXBatch];
+#pragma unroll
+            for (int u = 0; u < kSkXBatch; ++u)
+                if (i0 + u * NT < total) v[u] = ldg_nc_v4(x + (size_t)(i0 + u * NT) * VEC);
+#pragma unroll
+            for (int u = 0; u < kSkXBatch; ++u) {
+                const int i = i0 + u * NT;
+                if (i < total) { const int m = i / nvec; put(xs + (size_t)m * a.xp + (i - m * nvec) * 16, v[u]); }
+            }
+        }
     } else if (a.prologue == 1) {                                        // RMSNorm
         float ss[kSkMaxM];
 #pragma unroll
         for (int m = 0; m < kSkMaxM; ++m) ss[m] = 0.f;
+        for (int i0 = tid; i0 < total; i0 += NT * kSkXBatch) {
+            uint4 v[kSkXBatch];
 #pragma unroll
-        for (int m = 0; m < kSkMaxM; ++m) {
-            if (m >= a.M) break;
-            for (int j = tid; j < nvec; j += kSkThreads) {
-                float f[VEC];
-                Vec16<T>::unpack(ldg_nc_v4(x + (size_t)m * a.K + j * VEC), f);
+            for (int u = 0; u < kSkXBatch; ++u)
+                if (i0 + u * NT < total) v[u] = ldg_nc_v4(x + (size_t)(i0 + u * NT) * VEC);
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) ss[m] = fmaf(f[k], f[k], ss[m]);
+            for (int u = 0; u < kSkXBatch; ++u) {
+                const int i = i0 + u * NT;
+                if (i < total) {
+                    float f[VEC], sq = 0.f;
+                    Vec16<T>::unpack(v[u], f);
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) sq = fmaf(f[k], f[k], sq);
+                    const int m = i / nvec;
+#pragma unroll
+                    for (int mm = 0; mm < kSkMaxM; ++mm) ss[mm] += (m == mm) ? sq : 0.f;
+                }
             }
         }
 #pragma unroll
@@ -134,34 +163,70 @@ __device__ __forceinline__ void sk_stage_x(const SkinnyArgs &a, uint8_t *xs, flo
             for (int o = 16; o > 0; o >>= 1) ss[m] += __shfl_xor_sync(0xffffffffu, ss[m], o);
             if ((tid & 31) == 0) s_red[(tid >> 5) * kSkMaxM + m] = ss[m];
         }
-        __syncthreads();
-        const T *nw = static_cast<const T *>(a.norm_w);
+        sync_all();
+        float rstd[kSkMaxM];
 #pragma unroll
         for (int m = 0; m < kSkMaxM; ++m) {
-            if (m >= a.M) break;
             float tot = 0.f;
+            for (int w = 0; w < NT / 32; ++w) tot += s_red[w * kSkMaxM + m];
+            rstd[m] = rsqrtf(tot / (float)a.K + a.eps);
+        }
+        const T *nw = static_cast<const T *>(a.norm_w);
+        for (int i0 = tid; i0 < total; i0 += NT * kSkXBatch) {          // second pass: x again (L2) + the norm weights
+            uint4 v[kSkXBatch], wv[kSkXBatch];
+            int mi[kSkXBatch];
 #pragma unroll
-            for (int w = 0; w < kSkWarps; ++w) tot += s_red[w * kSkMaxM + m];
-            const float r = rsqrtf(tot / (float)a.K + a.eps);
-            for (int j = tid; j < nvec; j += kSkThreads) {
-                float f[VEC], g[VEC], o[VEC];
-                Vec16<T>::unpack(ldg_nc_v4(x + (size_t)m * a.K + j * VEC), f);
-                Vec16<T>::unpack(ldg_nc_v4(nw + j * VEC), g);
+            for (int u = 0; u < kSkXBatch; ++u) {
+                const int i = i0 + u * NT;
+                if (i < total) {
+                    mi[u] = i / nvec;
+                    v[u] = ldg_nc_v4(x + (size_t)i * VEC);
+                    wv[u] = ldg_nc_v4(nw + (size_t)(i - mi[u] * nvec) * VEC);
+                }
+            }
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) o[k] = g[k] * sk_rnd<T>(f[k] * r);
-                *reinterpret_cast<uint4 *>(xs + (size_t)m * a.xp + j * 16) = sk_perm(Vec16<T>::pack(o));
+            for (int u = 0; u < kSkXBatch; ++u) {
+                const int i = i0 + u * NT;
+                if (i < total) {
+                    float r = 0.f;
+#pragma unroll
+                    for (int mm = 0; mm < kSkMaxM; ++mm) r = (mi[u] == mm) ? rstd[mm] : r;
+                    float f[VEC], g[VEC], o[VEC];
+                    Vec16<T>::unpack(v[u], f);
+                    Vec16<T>::unpack(wv[u], g);
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) o[k] = g[k] * sk_rnd<T>(f[k] * r);
+                    put(xs + (size_t)mi[u] * a.xp + (i - mi[u] * nvec) * 16, Vec16<T>::pack(o));
+                }
             }
         }
     } else {                                                             // SwiGLU of [gate | up] rows of 2K columns
-        for (int m = 0; m < a.M; ++m)
-            for (int j = tid; j < nvec; j += kSkThreads) {
-                float g[VEC], u[VEC], o[VEC];
-                Vec16<T>::unpack(ldg_nc_v4(x + (size_t)m * 2 * a.K + j * VEC), g);
-                Vec16<T>::unpack(ldg_nc_v4(x + (size_t)m * 2 * a.K + a.K + j * VEC), u);
+        for (int i0 = tid; i0 < total; i0 += NT * kSkXBatch) {
+            uint4 gv[kSkXBatch], uv[kSkXBatch];
+            int mi[kSkXBatch];
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) o[k] = sk_rnd<T>(sk_silu(g[k])) * u[k];
-                *reinterpret_cast<uint4 *>(xs + (size_t)m * a.xp + j * 16) = sk_perm(Vec16<T>::pack(o));
+            for (int u = 0; u < kSkXBatch; ++u) {
+                const int i = i0 + u * NT;
+                if (i < total) {
+                    mi[u] = i / nvec;
+                    const T *row = x + (size_t)mi[u] * 2 * a.K + (size_t)(i - mi[u] * nvec) * VEC;
+                    gv[u] = ldg_nc_v4(row);
+                    uv[u] = ldg_nc_v4(row + a.K);
+                }
             }
+#pragma unroll
+            for (int u = 0; u < kSkXBatch; ++u) {
+                const int i = i0 + u * NT;
+                if (i < total) {
+                    float g[VEC], up[VEC], o[VEC];
+                    Vec16<T>::unpack(gv[u], g);
+                    Vec16<T>::unpack(uv[u], up);
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) o[k] = sk_rnd<T>(sk_silu(g[k])) * up[k];
+                    put(xs + (size_t)mi[u] * a.xp + (i - mi[u] * nvec) * 16, Vec16<T>::pack(o));
+                }
+            }
+        }
     }
 }
 
@@ -244,7 +309,7 @@ __global__ void __launch_bounds__(kSkThreads, 1) linear_skinny_kernel(const __gr
 #pragma unroll
     for (int i = 0; i < DEPTH; ++i) request();
 
-    sk_stage_x<T>(a, xs, s_red, tid);                     // overlaps the first DEPTH steps of copies
+    sk_stage_x<T, kSkThreads, true>(a, xs, s_red, tid);   // overlaps the first DEPTH steps of copies
     __syncthreads();
 
     // ---- compute cursor ------------------------------------------------------------------------------------------------
@@ -297,6 +362,222 @@ __global__ void __launch_bounds__(kSkThreads, 1) linear_skinny_kernel(const __gr
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// The same op fed by tensor-map TMA (what the library's own skinny kernels do): one cp.async.bulk.tensor.2d per
+// (128 rows x 64 columns) = 16 KB box of W, SWIZZLE_128B, into a ring of up to 11 stages (176 KB in flight per SM, no
+// per-lane copy instructions, no L1 involvement).  Stream-K over (128-row block, 64-column step) units; warp w of the 8
+// consumer warps owns rows 16w .. 16w+15 of the block for ALL its K steps (ldmatrix.x4 from the swizzled stage as the A
+// fragment, x from shared memory as the B fragment, fp32 accumulators in registers), so a block needs no cross-warp
+// reduction.  A block cut by range boundaries leaves per-CTA partial tiles (at most two per CTA: its first and its last
+// block) and the last CTA to arrive adds them in CTA order.
+constexpr int kTmRows = 128, kTmCols = 64, kTmStage = kTmRows * kTmCols * 2, kTmWarps = 8, kTmThreads = (kTmWarps + 1) * 32;
+constexpr int kTmTile = kTmRows * 8;                      // fp32 outputs of a block
+constexpr int kTmMaxStages = 12, kTmMaxCtas = 256;
+
+static __device__ unsigned long long g_sk_dbg[4 * 256];
+__device__ __forceinline__ unsigned long long sk_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void tm_consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void tm_ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTmThreads, 1)
+linear_skinny_tma_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ SkinnyArgs a, int n_stages) {
+    extern __shared__ __align__(1024) uint8_t s_tm[];
+    // layout: W ring [n_stages][16 KB] (1024-byte aligned for the swizzle) | x rows | rmsnorm scratch | barriers | flag
+    uint8_t *ring = s_tm;
+    uint8_t *xs = ring + (size_t)n_stages * kTmStage;
+    float *s_red = reinterpret_cast<float *>(xs + (size_t)a.M * a.xp);
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_red + kTmWarps * kSkMaxM);
+    uint64_t *empty = full + kTmMaxStages;
+    int *s_flag = reinterpret_cast<int *>(empty + kTmMaxStages);
+    if ((s_addr(s_tm) & 1023u) != 0u) { asm volatile("trap;"); }
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c = blockIdx.x;
+    const int f0 = sk_range_start(c, a.q, a.rm), n_my = sk_range_start(c + 1, a.q, a.rm) - f0;
+    if (a.dbg != nullptr && tid == 0) a.dbg[c * 4 + 0] = sk_now();
+
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) { bar_init(full + s, 1); bar_init(empty + s, kTmWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kTmWarps) {
+        // ======================================= producer =======================================
+        if (lane == 0) {
+            int s = 0, round = 0, blk = f0 / a.spb, kc = f0 - blk * a.spb;
+            for (int it = 0; it < n_my; ++it) {
+                if (round > 0) bar_wait(empty + s, (round - 1) & 1);
+                bar_expect_tx(full + s, kTmStage);
+                tma_load_2d(ring + (size_t)s * kTmStage, &map_w, full + s, kc * kTmCols, blk * kTmRows);
+                if (++s == n_stages) { s = 0; ++round; }
+                if (++kc == a.spb) { kc = 0; ++blk; }
+            }
+        }
+        return;
+    }
+
+    // ========================================= consumers =========================================
+    sk_stage_x<T, 256, false>(a, xs, s_red, tid);          // while the producer already streams W
+    tm_consumer_sync();
+
+    const int g = lane >> 2, t = lane & 3;
+    // ldmatrix.x4 lane -> (row, k half) of the 16 x 16 tile: lanes 0-7 rows 0-7 / k 0-7, 8-15 rows 8-15 / k 0-7,
+    // 16-23 rows 0-7 / k 8-15, 24-31 rows 8-15 / k 8-15; a 16-byte chunk c of row r sits at chunk c ^ (r & 7) (SWIZZLE_128B)
+    const int lr = (lane & 7) + ((lane >> 3) & 1) * 8, lhi = lane >> 4;
+    const uint32_t row_off = (uint32_t)((warp * 16 + lr) * 128);
+    const uint32_t ring_addr = s_addr(ring);
+    const uint8_t *xb = xs + (size_t)(g < a.M ? g : 0) * a.xp + 2 * t * 2;      // x[g][k + 2t], x[g][k + 2t + 8]
+    T *y = static_cast<T *>(a.y);
+    const T *res = static_cast<const T *>(a.residual);
+
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    int s = 0, round = 0, blk = f0 / a.spb, kc = f0 - blk * a.spb;
+    const int my_first_blk = blk;
+    for (int it = 0; it < n_my; ++it) {
+        bar_wait(full + s, round & 1);
+        if (a.dbg != nullptr && tid == 0 && (it == 0 || it == n_my - 1)) a.dbg[c * 4 + (it == 0 ? 1 : 2)] = sk_now();
+        const uint32_t st = ring_addr + (uint32_t)s * kTmStage + row_off;
+        const uint8_t *xk = xb + (size_t)kc * (kTmCols * 2);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            uint32_t af[4];
+            tm_ldmatrix_x4(af, st + (uint32_t)(((kk * 2 + lhi) ^ (lr & 7)) << 4));
+            const uint32_t b0 = *reinterpret_cast<const uint32_t *>(xk + kk * 32);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t *>(xk + kk * 32 + 16);
+            SkMma<T>::mma(d, af, b0, b1);
+        }
+        __syncwarp();
+        if (lane == 0) bar_arrive(empty + s);
+        if (++s == n_stages) { s = 0; ++round; }
+
+        const bool block_ends = (kc == a.spb - 1) || (it == n_my - 1);
+        const int this_blk = blk;
+        if (++kc == a.spb) { kc = 0; ++blk; }
+        if (!block_ends) continue;
+        // ---- this CTA's share of block `this_blk`: the lane holds (row g / g + 8 of the warp's 16, x rows 2t, 2t + 1) ------
+        const int first = this_blk * a.spb, last = first + a.spb - 1;
+        const int c_first = sk_cta_of(first, a.q, a.rm), c_last = sk_cta_of(last, a.q, a.rm);
+        const int r0 = warp * 16 + g;
+        float v[4] = {d[0], d[1], d[2], d[3]};
+        d[0] = d[1] = d[2] = d[3] = 0.f;
+        bool finish = true;
+        if (c_first != c_last) {                                              // cut: per-CTA partial tiles + a ticket
+            float *mine = a.part + ((size_t)c * 2 + (this_blk == my_first_blk ? 0 : 1)) * kTmTile;
+            mine[r0 * 8 + 2 * t] = v[0];
+            mine[r0 * 8 + 2 * t + 1] = v[1];
+            mine[(r0 + 8) * 8 + 2 * t] = v[2];
+            mine[(r0 + 8) * 8 + 2 * t + 1] = v[3];
+            __threadfence();
+            tm_consumer_sync();
+            if (tid == 0) *s_flag = atomicAdd(a.tickets + this_blk, 1u) == (unsigned)(c_last - c_first);
+            tm_consumer_sync();
+            finish = *s_flag != 0;
+            if (finish) {
+                __threadfence();
+                v[0] = v[1] = v[2] = v[3] = 0.f;
+                for (int cc = c_first; cc <= c_last; ++cc) {                  // CTA order: timing-independent
+                    const int cc_first_blk = sk_range_start(cc, a.q, a.rm) / a.spb;
+                    const float *pp = a.part + ((size_t)cc * 2 + (this_blk == cc_first_blk ? 0 : 1)) * kTmTile;
+                    v[0] += __ldcg(pp + r0 * 8 + 2 * t);
+                    v[1] += __ldcg(pp + r0 * 8 + 2 * t + 1);
+                    v[2] += __ldcg(pp + (r0 + 8) * 8 + 2 * t);
+                    v[3] += __ldcg(pp + (r0 + 8) * 8 + 2 * t + 1);
+                }
+                if (tid == 0) a.tickets[this_blk] = 0u;                       // zero on entry, zero on exit
+            }
+            tm_consumer_sync();                                               // s_flag may be rewritten by the next block
+        }
+        if (finish) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int m = 2 * t + (e & 1), row = r0 + (e >> 1) * 8;
+                if (m < a.M) {
+                    const size_t o = (size_t)m * a.N + (size_t)this_blk * kTmRows + row;
+                    float out = v[e];
+                    if (res != nullptr) out += to_op(res[o]);
+                    y[o] = from_op<T>(out);
+                }
+            }
+        }
+    }
+    if (a.dbg != nullptr && tid == 0) a.dbg[c * 4 + 3] = sk_now();
+}
+
+static inline size_t skinny_tma_smem(int stages, int M, int K) {
+    return (size_t)stages * kTmStage + (size_t)M * (K * 2 + 16) + kTmWarps * kSkMaxM * sizeof(float) + 2 * kTmMaxStages * sizeof(uint64_t) + 16;
+}
+
+struct SkMapKey { const void *ptr; int dtype, N, K; };
+static thread_local SkMapKey g_sk_keys[16];
+static thread_local CUtensorMap g_sk_maps[16];
+static thread_local int g_sk_n = 0, g_sk_next = 0;
+
+static int skinny_weight_map(CUtensorMap *map, const void *w, int dtype, int N, int K) {
+    for (int i = 0; i < g_sk_n; ++i)
+        if (g_sk_keys[i].ptr == w && g_sk_keys[i].dtype == dtype && g_sk_keys[i].N == N && g_sk_keys[i].K == K) { *map = g_sk_maps[i]; return MMFS_OK; }
+    EncodeTiledFn fn = tensor_map_encoder();
+    if (!fn) { set_error("linear_skinny: cuTensorMapEncodeTiled is not available from this driver"); return MMFS_ECUDA; }
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    const cuuint32_t box[2] = {kTmCols, kTmRows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, dtype == MMFS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                    const_cast<void *>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("linear_skinny: cuTensorMapEncodeTiled failed (%d)", (int)r); return MMFS_ECUDA; }
+    g_sk_keys[g_sk_next] = SkMapKey{w, dtype, N, K};
+    g_sk_maps[g_sk_next] = *map;
+    g_sk_next = (g_sk_next + 1) % 16;
+    if (g_sk_n < 16) ++g_sk_n;
+    return MMFS_OK;
+}
+
+template <typename T>
+static int launch_skinny_tma(SkinnyArgs a, int dtype, cudaStream_t st) {
+    CUtensorMap map;
+    int rc = skinny_weight_map(&map, a.w, dtype, a.N, a.K);
+    if (rc != MMFS_OK) return rc;
+    const int n_blocks = a.N / kTmRows;
+    a.xp = a.K * 2 + 16;
+    a.spb = a.K / kTmCols;
+    a.total = n_blocks * a.spb;
+    int grid = num_sms();
+    if (grid > kTmMaxCtas) grid = kTmMaxCtas;
+    if (grid > a.total) grid = a.total;
+    a.q = a.total / grid;
+    a.rm = a.total % grid;
+    int stages = kTmMaxStages;
+    while (stages > 3 && skinny_tma_smem(stages, a.M, a.K) + 1024 > (size_t)kSkMaxSmem) --stages;
+    if (skinny_tma_smem(stages, a.M, a.K) + 1024 > (size_t)kSkMaxSmem) {
+        set_error("linear_skinny: M = %d rows of K = %d do not fit shared memory next to a 3-stage weight ring", a.M, a.K);
+        return MMFS_EUNSUPPORTED;
+    }
+    if (stages > a.q + 1) stages = a.q + 1;
+    auto kern = linear_skinny_tma_kernel<T>;
+    static bool attr_set[kMaxDevices] = {};
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDevices || !attr_set[dev]) {
+        MMFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkMaxSmem));
+        if (dev >= 0 && dev < kMaxDevices) attr_set[dev] = true;
+    }
+    kern<<<grid, kTmThreads, skinny_tma_smem(stages, a.M, a.K), st>>>(map, a, stages);
+    MMFS_CUDA(cudaGetLastError());
+    return MMFS_OK;
+}
+
+static bool g_sk_probe = false;
+static int g_sk_mode = 0;   // 0 / 2: tensor-map TMA kernel when the shape allows; 1: per-lane cp.async kernel
+
 static inline size_t skinny_smem(int depth, int M, int K) {
     return (size_t)depth * kSkSlotBytes + (size_t)M * (K * 2 + kSkXPad) + (kSkWarps * kSkTile + kSkWarps * kSkMaxM) * sizeof(float) + 16;
 }
@@ -342,7 +623,24 @@ extern "C" long mmfs_linear_skinny_scratch_floats(int N) {
     const long n_blocks = (N + kSkRows - 1) / kSkRows;
     // tickets at a FIXED place (the head) whatever N is -- a buffer shared between calls of different N must never see
     // one call's partial tiles where another call expects zero tickets -- then two partial tiles per block
-    return kSkMaxBlocks + n_blocks * 2 * kSkTile;
+    const long lanes = kSkMaxBlocks + n_blocks * 2 * kSkTile;                // per-lane cp.async kernel: two tiles per 32-row block
+    const long boxes = kSkMaxBlocks + (long)kTmMaxCtas * 2 * kTmTile;        // tensor-map kernel: two tiles per CTA
+    return lanes > boxes ? lanes : boxes;
+}
+
+extern "C" int mmfs_linear_skinny_set_tuning(int mode) {
+    MMFS_CHECK_ARG((mode & 3) <= 2 && mode >= 0 && mode < 8, "linear_skinny_set_tuning: 0 default, 1 per-lane cp.async kernel, 2 tensor-map TMA kernel, +4 timing probe");
+    g_sk_mode = mode & 3;
+    g_sk_probe = (mode & 4) != 0;
+    return MMFS_OK;
+}
+
+/* timing probe (mode + 4, tensor-map kernel): per CTA {entry, first stage landed, last stage landed, exit} in globaltimer ns */
+extern "C" int mmfs_linear_skinny_probe(unsigned long long *host_out, int n_ctas) {
+    MMFS_CHECK_ARG(host_out != nullptr && n_ctas > 0 && n_ctas <= 256, "linear_skinny_probe: bad arguments");
+    MMFS_CUDA(cudaDeviceSynchronize());
+    MMFS_CUDA(cudaMemcpyFromSymbol(host_out, g_sk_dbg, sizeof(unsigned long long) * 4 * n_ctas));
+    return MMFS_OK;
 }
 
 extern "C" int mmfs_linear_skinny(const void *x, const void *w, void *y, const void *residual, const void *norm_weight,
@@ -362,6 +660,11 @@ extern "C" int mmfs_linear_skinny(const void *x, const void *w, void *y, const v
     a.tickets = reinterpret_cast<unsigned *>(scratch);
     a.part = scratch + kSkMaxBlocks;
     a.M = M; a.N = N; a.K = K; a.prologue = prologue; a.eps = eps;
+    a.dbg = nullptr;
+    if (g_sk_probe) MMFS_CUDA(cudaGetSymbolAddress((void **)&a.dbg, g_sk_dbg));
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_sk_mode != 1 && N % kTmRows == 0 && K % kTmCols == 0 && N / kTmRows <= kSkMaxBlocks &&
+        skinny_tma_smem(3, M, K) + 1024 <= (size_t)kSkMaxSmem)
+        return dtype == MMFS_F16 ? launch_skinny_tma<__half>(a, dtype, st) : launch_skinny_tma<__nv_bfloat16>(a, dtype, st);
     return dtype == MMFS_F16 ? launch_skinny<__half>(a, st) : launch_skinny<__nv_bfloat16>(a, st);
 }

@@ -46,6 +46,10 @@ def timed(fn, reps=15):
     return ts[len(ts) // 2]
 
 
+from mm_interleaved_b200 import _lib  # noqa: E402
+MODE = int(os.environ.get("SK_MODE", 0))
+assert _lib.lib().mmfs_linear_skinny_set_tuning(MODE) == 0
+print(f"linear_skinny mode {MODE} (0 default, 1 per-lane cp.async, 2 tensor-map TMA)")
 tot_a = tot_b = 0.0
 with torch.no_grad():
     for name, N, K, pro, with_res in SHAPES:
