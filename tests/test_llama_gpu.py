@@ -213,6 +213,39 @@ def test_long_prompt_takes_the_tcgen05_kernel_and_tracks_the_reference_golden(dt
     assert err.pow(2).mean().sqrt() <= rms_tol * ref[valid].pow(2).mean().sqrt(), float(err.pow(2).mean().sqrt() / ref[valid].pow(2).mean().sqrt())
 
 
+FULL_WIDTH = dict(vocab_size=64, hidden_size=5120, intermediate_size=13824, num_hidden_layers=2, num_attention_heads=40,
+                  max_position_embeddings=2048, rms_norm_eps=1e-6, pad_token_id=0, cross_attention_frequency=2,
+                  spatial_shapes=[32, 16, 8], image_embed_dim=1024)
+
+
+@pytest.mark.parametrize("dtype,max_tol,rms_tol", [(torch.float32, 2e-4, 2e-5), (torch.bfloat16, 4e-2, 1.5e-2)])
+def test_full_width_layers_match_the_oracle(dtype, max_tol, rms_tol):
+    """Two decoder layers at the 13 B model's REAL widths (hidden 5120, 40 heads of 128, MLP 13824, MMFS with 16 heads x 64
+    over 32^2 + 16^2 + 8^2 feature maps of 3 images, seeded weights): one MMFS layer + one plain layer on a 160-token
+    left-padded prompt against the oracle restatement of the reference layers (oracle/llama.py, pinned by the tiny
+    goldens) on the host.  fp32 takes the bandwidth attention kernel and the generic sampler's fp32 path; bf16 the
+    tcgen05 kernel and the specialised 16-bit sampler -- the kernels and shapes of the benchmarked step."""
+    from oracle.llama import llama_model_ref
+    from mm_interleaved_b200.llama_mmfs import LlamaMMFSConfig, LlamaModel
+    model = LlamaModel(LlamaMMFSConfig(**FULL_WIDTH))
+    sd = seeded_state_dict(model.state_dict(), seed=777)
+    model.load_state_dict(sd, strict=True)
+    B, T, n_img = 2, 160, 3
+    embeds, vision, attn_mask, position_ids, cross = llama_inputs(FULL_WIDTH, B, T, n_img, seed=5, left_pad=7)
+    cfg = dict(eps=1e-6, n_heads=40, n_layers=2, spatial_shapes=[(s, s) for s in FULL_WIDTH["spatial_shapes"]])
+    ref, _ = llama_model_ref(sd, embeds, attn_mask, position_ids, vision, cross, cfg)
+    model = model.to(DEV, dtype).eval()
+    with torch.no_grad():
+        out = model(inputs_embeds=embeds.to(DEV, dtype), attention_mask=attn_mask.to(DEV), position_ids=position_ids.to(DEV),
+                    vision_hidden_states=vision.to(DEV, dtype), cross_attention_mask=cross.to(DEV), use_cache=False)
+    valid = attn_mask.bool()
+    got = out.last_hidden_state.float().cpu()
+    err = (got - ref)[valid]
+    assert torch.isfinite(got[valid]).all()
+    assert err.abs().max() <= max_tol * ref[valid].abs().max(), float(err.abs().max() / ref[valid].abs().max())
+    assert err.pow(2).mean().sqrt() <= rms_tol * ref[valid].pow(2).mean().sqrt(), float(err.pow(2).mean().sqrt() / ref[valid].pow(2).mean().sqrt())
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("cols", [64, 320, 768, 1024, 1280, 2048, 5120, 100])
 def test_layernorm_matches_torch(cols, dtype):
