@@ -464,10 +464,31 @@ def qformer_inputs(seed=43):
     return enc, mask
 
 
-def make_tokenizer():
+TOKENIZER_FULL = dict(clip=dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+                                image_size=224, patch_size=14),
+                      perceiver=dict(num_queries=64, hidden_size=768, encoder_hidden_size=1024, cross_attention_frequency=2,
+                                     num_hidden_layers=12, num_attention_heads=12, qk_normalization=True),
+                      llm_hidden_size=5120, grid_size=16)
+
+
+def tokenizer_full_inputs(seed=47):
+    return torch.rand((1, 3, 224, 224), generator=torch.Generator().manual_seed(seed))
+
+
+def tokenizer_full_slices(out):
+    """The entries of a full-size tokenizer output that the fixture keeps (the outputs are 30 MB): every 8th feature of
+    vis_embed / image_embeds, every 16th channel x every 2nd / 4th pixel of the four multi-scale maps."""
+    picks = {"vis_embed": out["vis_embed"][..., ::8], "image_embeds": out["image_embeds"][:, ::4, ::8]}
+    for i, f in enumerate(out["multiscale_features"]):
+        st = 4 if f.shape[-1] >= 32 else 2
+        picks[f"ms{i}"] = f[:, ::16, ::st, ::st]
+    return picks
+
+
+def make_tokenizer(full=False):
     from transformers import CLIPVisionConfig
     ns = ref_loader.load_visual()
-    c = TOKENIZER_TINY
+    c = TOKENIZER_FULL if full else TOKENIZER_TINY
     cfg = CLIPVisionConfig(**c["clip"], hidden_act="quick_gelu", layer_norm_eps=1e-5)
     cfg._attn_implementation = "eager"
 
@@ -484,6 +505,14 @@ def make_tokenizer():
                                               grid_size=c["grid_size"]).eval()
     sd = tokenizer_state_dict(tok.state_dict())
     tok.load_state_dict(sd)
+    if full:        # CLIP ViT-L/14 at 224^2 + ViT-Adapter + 12-layer Q-Former, the shapes of the benchmarked step
+        with torch.no_grad():
+            out = tok(tokenizer_full_inputs())
+        path = os.path.join(HERE, "tokenizer_full.npz")
+        np.savez_compressed(path, **{k: v.numpy().astype(np.float32) for k, v in tokenizer_full_slices(out).items()},
+                            n_keys=np.array(len(sd)), checksum=np.array(float(sum(v.double().sum() for v in sd.values()))))
+        print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB")
+        return
     with torch.no_grad():
         out = tok(tokenizer_inputs())
     path = os.path.join(HERE, "tokenizer_tiny.npz")
@@ -514,6 +543,8 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["msda", "mmfs", "llama", "mmfsnet", "adapter", "imgdec", "tokenizer"]
     if "tokenizer" in which:
         make_tokenizer()
+    if "tokenizer_full" in which:
+        make_tokenizer(full=True)
     if "imgdec" in which:
         make_imgdec()
     if "adapter" in which:
