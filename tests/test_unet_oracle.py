@@ -132,3 +132,49 @@ def test_full_width_blocks_bf16_kernels_vs_oracle():
         err = (got.float().cpu() - want).abs()
         assert float(err.max()) <= 3e-2 * float(want.abs().max()), (float(err.max()), float(want.abs().max()))
         assert float(err.mean()) <= 4e-3 * float(want.abs().max())
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_full_sd21_unet_with_mmfs_hook_bf16_vs_oracle():
+    """The WHOLE SD-2.1 UNet (320 / 640 / 1280 / 1280 channels, 5 / 10 / 20 / 20 heads, 1024-wide context, 64 x 64 latents)
+    with the full-size MMFSNet hook (4 feature maps 64 / 32 / 16 / 8 of one context image), one evaluation in bf16 on this
+    repo's kernels against the fp32 oracle (oracle/unet.py + oracle/sd_mmfs.py) on the same bf16-rounded weights: the
+    network of BASELINE cfg 4, every skip connection, down / up-sampler and attention head count included."""
+    import mm_interleaved_b200 as m
+    from mm_interleaved_b200 import unet_sd
+    from oracle.sd_mmfs import mmfsnet_ref
+    torch.manual_seed(5)
+    unet = unet_sd.UNet2DConditionModel().eval()
+    net = m.MMFSNet(1024, (320, 640, 1280, 1280), 2, downsample_factor=1, spatial_shapes=[64, 32, 16, 8]).eval()
+    with torch.no_grad():
+        for blk in list(net.mmfs_down_blocks) + [net.mmfs_mid_block]:
+            blk.conv.weight.normal_(0, 0.05)                  # zero-initialised in the reference: make the hook count
+        for p_ in unet.parameters():
+            if p_.dim() == 1:
+                p_.add_(0.05 * torch.randn_like(p_))
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn((1, 4, 64, 64), generator=g)
+    ctx = torch.randn((1, 77, 1024), generator=g)
+    feats = [torch.randn((1, 1, 1024, s_, s_), generator=g) for s_ in (64, 32, 16, 8)]
+    mask = torch.ones((1, 1))
+    bf = lambda t_: t_.to(torch.bfloat16).float()
+    sd = {k: bf(v.detach()) for k, v in unet.state_dict().items()}
+    nsd = {k: bf(v.detach()) for k, v in net.state_dict().items()}
+    hook = lambda s_, res, f, mk: mmfsnet_ref(nsd, s_, list(res), f, mk, downsample_factor=1, n_down=len(res))
+    t = torch.tensor(421)
+    want = unet_forward_ref(sd, bf(x), t, bf(ctx), mmfs_features=[bf(f) for f in feats], mmfs_mask=mask, mmfs_module=hook)
+    want_plain = unet_forward_ref(sd, bf(x), t, bf(ctx))
+    assert float((want - want_plain).abs().max()) > 1e-2 * float(want.abs().max())      # the hook is live
+    dt = torch.bfloat16
+    dev = unet.cuda().to(dt).to(memory_format=torch.channels_last)
+    dnet = net.cuda().to(dt)
+    with torch.no_grad():
+        got = dev(x.cuda().to(dt).contiguous(memory_format=torch.channels_last), t.cuda(), ctx.cuda().to(dt),
+                  mmfs_features=[f.cuda().to(dt) for f in feats], mmfs_mask=mask.cuda(), mmfs_module=dnet)
+    err = (got.float().cpu() - want).abs()
+    scale = float(want.abs().max())
+    assert torch.isfinite(got.float()).all()
+    assert float(err.max()) <= 6e-2 * scale, (float(err.max()), scale)
+    rel_rms = float(err.pow(2).mean().sqrt() / want.pow(2).mean().sqrt())
+    assert rel_rms <= 3e-2, rel_rms          # bf16 storage at ~60 layer boundaries against an fp32 oracle
