@@ -597,6 +597,7 @@ class SdCfg4(Workload):
         self.B = self.local_batch or 8
         dt = torch.bfloat16
         self.sd = full_model().image_decoder.decoder                       # StableDiffusion: unet + mmfs_module + scheduler
+        self.sd.enable_cuda_graphs(True)                                   # one UNet graph, kept across generate_images calls
         g = torch.Generator().manual_seed(42 + self.rank)                  # sd_base_seed: 42 (mm_inference.yaml:23)
         mk = lambda: ([torch.randn((self.B, 4, 64, 64), generator=g), torch.randn((self.B, 77, 1024), generator=g) * 0.02] +
                       [torch.randn((self.B, 1, 1024, s, s), generator=g) for s in (64, 32, 16, 8)])
@@ -672,6 +673,16 @@ class SdCfg4(Workload):
 
     def kernel_stats(self):
         torch.cuda.synchronize()
+        if not self._conv_events:
+            # the timed steps replayed a CUDA graph (nothing to wrap): time the same kernels in a few EAGER evaluations of
+            # the same loop, outside the timed region
+            graphs, self.sd._unet_graphs = self.sd._unet_graphs, None
+            steps, self.STEPS = self.STEPS, 4
+            try:
+                self._run(self.dev_sets[0])
+            finally:
+                self.sd._unet_graphs, self.STEPS = graphs, steps
+            torch.cuda.synchronize()
         t = [a.elapsed_time(b) for a, b in self._attn_events]
         c = [a.elapsed_time(b) for a, b in self._conv_events]
         return {"launches": len(c), "avg_ms": sum(c) / len(c) if c else None,
@@ -684,6 +695,9 @@ class SdCfg4(Workload):
                             "attention, LayerNorm, MMFS = this repo's kernels; conv_in/conv_out + Linear GEMMs = cuDNN/cuBLAS; VAE not run",
                 "step_unit": f"one {self.STEPS}-step denoise of the rank-local batch of {self.B} images (2B UNet rows for CFG)",
                 "images_per_step": self.B, "global_batch": self.B * self.world, "parallelism": f"dp{self.world}",
+                "cuda_graph": "UNet evaluation captured once per shape and kept across generate_images calls "
+                              "(StableDiffusion.enable_cuda_graphs); per call the context, mask and MMFS image-side state are "
+                              "refreshed in place; scheduler steps eager; roofline kernels timed in separate eager evaluations",
                 "l2": "192 MiB buffer written between timed steps"}
 
     def roofline(self, kernel):
@@ -812,7 +826,8 @@ class GenerateCfg5(Workload):
                             f"out) on one {self.N_IMG}-image / {self.T}-token interleaved context per call (inference.py:237-269)",
                 "step_unit": "one sample: one generate_texts call + one generate_images call (batch 1)",
                 "global_batch": self.world, "seq_len": self.T, "images_per_seq": self.N_IMG, "parallelism": f"dp{self.world}",
-                "cuda_graph": "visual tokenizer graph + one decode-step graph replayed per generated token (enable_decode_graphs)",
+                "cuda_graph": "visual tokenizer graph + one decode-step graph replayed per generated token (enable_decode_graphs) + "
+                              "the UNet evaluation graph kept across calls",
                 "l2": "192 MiB buffer written between timed steps"}
 
     def roofline(self, kernel):

@@ -209,6 +209,13 @@ class StableDiffusion(nn.Module):
         self.image_size, self.base_seed, self.use_random_seed = image_size, base_seed, use_random_seed
         self.noise_scheduler = noise_scheduler if noise_scheduler is not None else DDPMScheduler(**SD21_BASE_SCHEDULER)
         self.vae_decode, self.vae_scaling_factor = vae_decode, vae_scaling_factor
+        self._unet_graphs = None        # enable_cuda_graphs(): {input shapes -> unet_sd.GraphedUNet}, kept across calls
+
+    def enable_cuda_graphs(self, on: bool = True):
+        """Replay the UNet evaluation (~1200 kernels) from a CUDA graph captured once per input shape and kept across
+        ``generate_images`` calls; the per-call MMFS image-side state is refreshed in place."""
+        self._unet_graphs = {} if on else None
+        return self
 
     @torch.no_grad()
     def generate_images(self, text_embeds, negative_prompt_embeds=None, num_validation_images=1, num_inference_steps=30,
@@ -237,7 +244,7 @@ class StableDiffusion(nn.Module):
                                    [f[sl] for f in mmfs_features] if mmfs_features is not None else None,
                                    mmfs_mask[sl] if mmfs_mask is not None else None, self.mmfs_module,
                                    num_steps=num_inference_steps, guidance=guidance_scale, scheduler=self.noise_scheduler,
-                                   generator=gen)
+                                   generator=gen, graph_cache=self._unet_graphs)
                 outs.append(lat)
         lat = torch.cat(outs, dim=0)
         if self.vae_decode is None:
@@ -760,6 +767,9 @@ class MMInterleaved(InterleavedForward):
         the next call overwrites -- everything this class returns to the caller is cloned out of them."""
         from ._graphs import GraphedCallable
         self._tok_graph = GraphedCallable(self.visual_tokenizer) if tokenizer else None
+        sd = getattr(getattr(self, "image_decoder", None), "decoder", None)
+        if sd is not None and hasattr(sd, "enable_cuda_graphs"):
+            sd.enable_cuda_graphs(True)                  # UNet evaluation graph, kept across generate_images calls
         return self
 
     def _tokenize(self, image_tensors):

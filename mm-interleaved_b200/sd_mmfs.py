@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import math
 from functools import partial
-from typing import List
+from typing import List, Optional
 
 import numpy as np
 import torch
@@ -133,19 +133,40 @@ class MMFSBlock(nn.Module):
                 self._feat_cache.put(ms_feat, hit, extra)
         return hit
 
-    def forward(self, sample, ms_feat, ms_feat_mask, spatial_shapes):
-        """sample (B, C_q, H, W); ms_feat (B, N, sum(H_l*W_l), C_v); ms_feat_mask (B, N); returns the residual (B, C_q, H, W)."""
+    @torch.no_grad()
+    def project_features(self, ms_feat):
+        """value_proj(LayerNorm(ms_feat)) in the sampler's (B, N*HW, heads, D) layout: everything this block derives from
+        the feature maps alone (constant over the denoise steps of a loop)."""
+        return self.mmfs.project_value(self.normalised_features(ms_feat))
+
+    def forward(self, sample, ms_feat, ms_feat_mask, spatial_shapes, value=None):
+        """sample (B, C_q, H, W); ms_feat (B, N, sum(H_l*W_l), C_v); ms_feat_mask (B, N); returns the residual (B, C_q, H, W).
+        ``value`` (extension): ``project_features(ms_feat)`` computed by the caller (``ms_feat`` is then not read)."""
         B, C, H, W = sample.shape
         n_images = ms_feat_mask.shape[-1]
         ref, ss, starts, pos = self._geometry(sample.device, sample.dtype, H, W, n_images, spatial_shapes)
         query = sample.flatten(2).transpose(1, 2).contiguous()                       # b c h w -> b (h w) c
         query = ops.layernorm(query, self.query_norm.weight, self.query_norm.bias, self.query_norm.eps) + pos
-        feat = self.normalised_features(ms_feat)
+        feat = None if value is not None else self.normalised_features(ms_feat)
         # MMFS up to the sampled features, then output_proj and the 1x1 conv as one fused linear
         w, b = self._out_conv_fused()
         out = self.mmfs(query, ref, feat, ss, starts, input_padding_mask=None, attention_mask=ms_feat_mask,
-                        output_weight=w, output_bias=b)
+                        output_weight=w, output_bias=b, value=value)
         return out.transpose(1, 2).reshape(B, C, H, W)
+
+
+class PreparedSDFeatures:
+    """Image-side state of the MMFSNet hook for ONE batch of context feature maps: per block,
+    value_proj(LayerNorm(features)) -- what the blocks derive from the feature maps alone.  ``MMFSNet.prepare`` fills it
+    once per denoise loop; passing it in place of the ``mmfs_features`` list makes the blocks read it instead of
+    recomputing (or memoising by tensor identity).  With ``out=`` the values are written into existing storage: the
+    static buffers a captured UNet graph reads (``unet_sd.GraphedUNet``)."""
+
+    __slots__ = ("spatial_shapes", "values")
+
+    def __init__(self, spatial_shapes, values):
+        self.spatial_shapes = list(spatial_shapes)      # [(H_l, W_l)] of the feature maps
+        self.values = list(values)                      # one per down block, then the mid block
 
 
 class MMFSNet(nn.Module):
@@ -171,9 +192,31 @@ class MMFSNet(nn.Module):
         self.mmfs_mid_block = block(block_out_channels[-1], -1, len(blocks))
         self._packed = SourceCache()       # the level-concatenated feature tensor, identity-checked (see _cache.py)
 
+    @torch.no_grad()
+    def prepare(self, mmfs_features: List[torch.Tensor], out: Optional[PreparedSDFeatures] = None) -> PreparedSDFeatures:
+        """Run the feature-only part of every block once (see ``PreparedSDFeatures``)."""
+        spatial_shapes = [(int(f.shape[-2]), int(f.shape[-1])) for f in mmfs_features]
+        feats = torch.cat([f.flatten(3).transpose(2, 3) for f in mmfs_features], dim=2).contiguous()   # b n (h w) c
+        blocks = list(self.mmfs_down_blocks) + [self.mmfs_mid_block]
+        if out is None:
+            return PreparedSDFeatures(spatial_shapes, [blk.project_features(feats) for blk in blocks])
+        if out.spatial_shapes != spatial_shapes:
+            raise ValueError("prepare(out=...): feature-map shapes differ from the prepared buffers")
+        for dst, blk in zip(out.values, blocks):
+            dst.copy_(blk.project_features(feats))
+        return out
+
     def forward(self, sample: torch.Tensor, down_block_res_samples: List[torch.Tensor],
-                mmfs_features: List[torch.Tensor], mmfs_mask: torch.Tensor):
+                mmfs_features, mmfs_mask: torch.Tensor):
+        """``mmfs_features``: the list of feature maps (reference signature) or a ``PreparedSDFeatures`` (extension)."""
         assert len(down_block_res_samples) == len(self.mmfs_down_blocks)
+        if isinstance(mmfs_features, PreparedSDFeatures):
+            pv = mmfs_features
+            new_res = ()
+            for res, blk, val in zip(down_block_res_samples, self.mmfs_down_blocks, pv.values):
+                new_res += (res + blk(res, None, mmfs_mask, pv.spatial_shapes, value=val),)
+            sample = sample + self.mmfs_mid_block(sample, None, mmfs_mask, pv.spatial_shapes, value=pv.values[-1])
+            return sample, new_res
         spatial_shapes = [(int(f.shape[-2]), int(f.shape[-1])) for f in mmfs_features]
         # constant across the denoise steps of one loop: the same list of tensor objects comes back every step
         feats = None if torch.is_grad_enabled() else self._packed.get(list(mmfs_features))

@@ -302,29 +302,46 @@ class UNet2DConditionModel(nn.Module):
 
 
 class GraphedUNet:
-    """One UNet evaluation captured in a CUDA graph and replayed for every denoise step of a loop.
+    """One UNet evaluation captured in a CUDA graph and replayed for every denoise step -- of every loop of the same
+    shape.
 
-    An evaluation is ~1200 launches of 5-100 us kernels; issued eagerly the host barely keeps ahead of the GPU (and
-    falls behind on a loaded host).  Only ``sample`` and ``timestep`` change between the steps of one loop, so they go
-    through static buffers; the context, the MMFS feature maps and the mask are the loop's own tensors and are read in
-    place.  The eager warm-up evaluation fills the per-loop caches (MMFS feature LayerNorm + value projection, conv
-    filter layouts), so the captured graph contains only the per-step work.  The returned tensor lives in the graph's
-    memory pool: consume it before the next call."""
+    An evaluation is ~1200 launches of 5-100 us kernels; issued eagerly, a third of the wall time of a step is launch
+    gaps (20 ms of kernels in 28 ms at batch 16).  Capturing + instantiating the graph costs ~400 ms, more than one
+    50-step loop saves, so the graph must outlive the loop: ``sample`` and ``timestep`` (per step) and the context, the
+    mask and the MMFS image-side state (per loop) all live in static buffers.  ``load`` refills the per-loop ones --
+    the image-side state through ``MMFSNet.prepare(features, out=...)``, i.e. recomputed eagerly into the storage the
+    graph reads -- and ``__call__`` replays.  The returned tensor lives in the graph's memory pool: consume it before
+    the next call."""
 
     def __init__(self, unet, sample, timestep, ctx, mmfs_features, mmfs_mask, mmfs_module):
+        self.unet, self.mmfs_module = unet, mmfs_module
         self.sample = sample.clone()
         self.t = timestep.clone()
-        kw = dict(mmfs_features=mmfs_features, mmfs_mask=mmfs_mask, mmfs_module=mmfs_module)
+        self.ctx = ctx.clone()
+        self.mask = mmfs_mask.clone() if mmfs_mask is not None else None
+        self.prepared = None
+        if mmfs_module is not None and mmfs_features is not None:
+            prep = getattr(mmfs_module, "prepare", None)
+            self.prepared = prep(mmfs_features) if prep is not None else mmfs_features      # plain callables: read in place
+        kw = dict(mmfs_features=self.prepared, mmfs_mask=self.mask, mmfs_module=mmfs_module)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            unet(self.sample, self.t, ctx, **kw)                       # warm-up: caches, cuBLAS / cuDNN handles
+            unet(self.sample, self.t, self.ctx, **kw)                  # warm-up: weight-derived caches, library handles
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         before = ops.launch_counter[0]
         with torch.cuda.graph(self.graph):
-            self.out = unet(self.sample, self.t, ctx, **kw)
+            self.out = unet(self.sample, self.t, self.ctx, **kw)
         self.launches = ops.launch_counter[0] - before                 # this repo's kernels inside one replay
+
+    def load(self, ctx, mmfs_features, mmfs_mask):
+        """New per-loop inputs (same shapes): context, mask and the MMFS image-side state."""
+        self.ctx.copy_(ctx)
+        if self.mask is not None:
+            self.mask.copy_(mmfs_mask)
+        if self.prepared is not None and hasattr(self.mmfs_module, "prepare"):
+            self.mmfs_module.prepare(mmfs_features, out=self.prepared)
 
     def __call__(self, sample, timestep):
         self.sample.copy_(sample)
@@ -336,14 +353,16 @@ class GraphedUNet:
 
 @torch.no_grad()
 def denoise_loop(unet, latents, cond, uncond, mmfs_features, mmfs_mask, mmfs_module, num_steps=50, guidance=7.5,
-                 num_train_timesteps=1000, cuda_graph: Optional[bool] = None, scheduler=None, generator=None):
+                 num_train_timesteps=1000, cuda_graph: Optional[bool] = None, scheduler=None, generator=None,
+                 graph_cache: Optional[dict] = None):
     """Classifier-free-guidance denoise loop in the shape of the patched pipeline ``__call__``
     (utils/monkey_patch/sd_pipeline_monkey_patch.py:153-218: ``set_timesteps``; CFG duplicates the MMFS inputs; per step
     ``scale_model_input``, one UNet call on the 2B batch, ``uncond + g (text - uncond)``, ``scheduler.step``).
     ``scheduler``: any object with ``set_timesteps / scale_model_input / step`` (scheduler.py; a diffusers scheduler
     works too).  Default = the reference's choice, DDPM ancestral sampling on the SD-2.1-base schedule (sd.py:48-50),
-    its noise drawn from ``generator``.  ``cuda_graph=True`` captures the UNet evaluation once per loop and replays it
-    per step (opt-in, see below)."""
+    its noise drawn from ``generator``.  ``graph_cache`` (a dict the caller keeps, e.g. ``StableDiffusion``): replay the
+    UNet evaluation from a CUDA graph captured once per input shape and kept across loops (``GraphedUNet``);
+    ``cuda_graph=True`` without a cache captures one graph for this loop only (costs more than it saves, see below)."""
     from .scheduler import DDPMScheduler, SD21_BASE_SCHEDULER
     if scheduler is None:
         scheduler = DDPMScheduler(**dict(SD21_BASE_SCHEDULER, num_train_timesteps=num_train_timesteps))
@@ -358,11 +377,17 @@ def denoise_loop(unet, latents, cond, uncond, mmfs_features, mmfs_mask, mmfs_mod
     feats2 = [torch.cat([f, f], 0) for f in mmfs_features] if mmfs_features is not None else None
     mask2 = torch.cat([mmfs_mask, mmfs_mask], 0) if mmfs_mask is not None else None
     if cuda_graph is None:
-        # Off by default: capturing + instantiating the ~1200-node graph costs ~400 ms per loop (measured, batch 16),
-        # more than the launch overhead it removes from 50 steps (1934 vs 1540 ms per loop).  It pays only when one
-        # captured graph serves many loops, which needs the per-loop MMFS feature caches refreshed in place.
-        cuda_graph = False
+        # Capturing + instantiating the ~1200-node graph costs ~400 ms (measured, batch 16) -- more than the launch
+        # overhead it removes from ONE 50-step loop (1934 vs 1540 ms) -- so a graph is used only when the caller keeps
+        # it across loops (graph_cache), with the per-loop MMFS state refreshed in place (GraphedUNet.load).
+        cuda_graph = graph_cache is not None and latents.is_cuda
     runner = None
+    if cuda_graph and graph_cache is not None:
+        key = (tuple(latents.shape), latents.dtype, tuple(ctx.shape), id(unet), id(mmfs_module),
+               None if feats2 is None else tuple(tuple(f.shape) for f in feats2), None if mask2 is None else tuple(mask2.shape))
+        runner = graph_cache.get(key)
+        if runner is not None:
+            runner.load(ctx, feats2, mask2)
     for i, t_host in enumerate(ts_host):
         t = ts_dev[i]
         x2 = scheduler.scale_model_input(torch.cat([latents, latents], 0), t)
@@ -371,6 +396,8 @@ def denoise_loop(unet, latents, cond, uncond, mmfs_features, mmfs_mask, mmfs_mod
         if cuda_graph:
             if runner is None:
                 runner = GraphedUNet(unet, x2, t, ctx, feats2, mask2, mmfs_module)
+                if graph_cache is not None:
+                    graph_cache[key] = runner
             eps = runner(x2, t)
         else:
             eps = unet(x2, t, ctx, mmfs_features=feats2, mmfs_mask=mask2, mmfs_module=mmfs_module)

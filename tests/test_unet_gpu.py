@@ -133,3 +133,63 @@ def test_graphed_denoise_loop_matches_eager():
     b = unet_sd.denoise_loop(unet, lat, cond, torch.zeros_like(cond), feats, mask, net, num_steps=4, cuda_graph=True,
                              scheduler=DDIMScheduler())
     assert torch.isfinite(a.float()).all() and (a.float() - b.float()).abs().max() <= 1e-2 * a.float().abs().max()
+
+
+def test_one_unet_graph_serves_loops_with_different_inputs():
+    """A graph_cache makes ``denoise_loop`` capture the UNet evaluation once and REUSE it for later loops of the same shape:
+    context, mask and the MMFS image-side state (MMFSNet.prepare(out=...)) are refreshed in place.  Two loops with different
+    context / feature maps / latents through one cached graph must give the eager results of their own inputs -- a stale
+    image-side buffer would reproduce the first loop's conditioning."""
+    import mm_interleaved_b200 as m
+    from mm_interleaved_b200 import unet_sd
+    from mm_interleaved_b200.scheduler import DDIMScheduler
+    torch.manual_seed(0)
+    unet = unet_sd.UNet2DConditionModel(block_out_channels=(320, 640), layers_per_block=1, attention_head_dim=(5, 10),
+                                        cross_attention_dim=128).to(DEV, torch.bfloat16).eval().to(memory_format=torch.channels_last)
+    net = m.MMFSNet(128, (320, 640), 1, downsample_factor=2, spatial_shapes=[32, 16, 8, 4]).to(DEV, torch.bfloat16).eval()
+    with torch.no_grad():
+        for blk in list(net.mmfs_down_blocks) + [net.mmfs_mid_block]:
+            blk.conv.weight.normal_(0, 0.2)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    mk = lambda: (torch.randn((2, 4, 32, 32), device=DEV, dtype=torch.bfloat16, generator=g),
+                  torch.randn((2, 7, 128), device=DEV, dtype=torch.bfloat16, generator=g),
+                  [torch.randn((2, 1, 128, s, s), device=DEV, dtype=torch.bfloat16, generator=g) for s in (32, 16, 8, 4)])
+    sets = [mk(), mk()]
+    mask = torch.ones((2, 1), device=DEV)
+    cache = {}
+    run = lambda st, gc: unet_sd.denoise_loop(unet, st[0], st[1], torch.zeros_like(st[1]), st[2], mask, net, num_steps=3,
+                                              scheduler=DDIMScheduler(), graph_cache=gc).float().clone()
+    eager = [run(st, None) for st in sets]
+    graphed = [run(sets[0], cache), run(sets[1], cache), run(sets[0], cache)]
+    assert len(cache) == 1                                   # one capture served all three loops
+    scale = eager[0].abs().max()
+    assert (eager[0] - eager[1]).abs().max() > 0.1 * scale   # the two input sets really differ
+    for got, want in zip(graphed, (eager[0], eager[1], eager[0])):
+        assert torch.isfinite(got).all() and (got - want).abs().max() <= 1e-2 * scale
+
+
+def test_prepared_sd_features_equal_the_list_form():
+    """MMFSNet with a PreparedSDFeatures (value_proj(LayerNorm(features)) computed once) = MMFSNet with the feature list."""
+    import mm_interleaved_b200 as m
+    torch.manual_seed(1)
+    net = m.MMFSNet(128, (320, 640), 1, downsample_factor=2, spatial_shapes=[32, 16, 8, 4]).to(DEV, torch.bfloat16).eval()
+    with torch.no_grad():
+        for blk in list(net.mmfs_down_blocks) + [net.mmfs_mid_block]:
+            blk.conv.weight.normal_(0, 0.2)
+    g = torch.Generator(device=DEV).manual_seed(4)
+    feats = [torch.randn((2, 1, 128, s, s), device=DEV, dtype=torch.bfloat16, generator=g) for s in (32, 16, 8, 4)]
+    like = lambda blk, side: torch.randn((2, blk.query_norm.normalized_shape[0], side, side), device=DEV, dtype=torch.bfloat16,
+                                         generator=g)               # a residual of the block's own width
+    res = [like(blk, 16 if i < 2 else 8) for i, blk in enumerate(net.mmfs_down_blocks)]   # conv_in, layer | downsampler, layer
+    sample = like(net.mmfs_mid_block, 8)
+    mask = torch.ones((2, 1), device=DEV)
+    with torch.no_grad():
+        a_s, a_r = net(sample, res, feats, mask)
+        pv = net.prepare(feats)
+        b_s, b_r = net(sample, res, pv, mask)
+        feats2 = [f * 0.5 + 1.0 for f in feats]
+        net.prepare(feats2, out=pv)                              # refreshed in place: same storage, new conditioning
+        c_s, _ = net(sample, res, pv, mask)
+        d_s, _ = net(sample, res, feats2, mask)
+    assert torch.equal(a_s, b_s) and all(torch.equal(x, y) for x, y in zip(a_r, b_r))
+    assert torch.equal(c_s, d_s) and not torch.equal(c_s, a_s)
