@@ -588,7 +588,7 @@ class SdCfg4(Workload):
     name = "sd_cfg4"
     metric = "sd_unet_denoise_steps_per_sec"
     STEPS = 50
-    default_steps, default_warmup = 2, 1
+    default_steps, default_warmup = 2, 2      # two warm-up loops: graph capture, then both input sets' first-use allocations
     CONV_SHAPE = (1280, 1280, 16, 3)          # Cin, Cout, map side, kernel: the conv timed for the roofline sub-object
 
     def setup(self):
@@ -735,7 +735,7 @@ class GenerateCfg5(Workload):
     metric = "generate_texts_plus_images_samples_per_sec"
     unit = "steps/s"
     T, N_IMG, TOK_PER_IMG, NEW_TOKENS, DENOISE = 1024, 8, 64, 30, 30
-    default_steps, default_warmup = 2, 1
+    default_steps, default_warmup = 2, 2      # graph captures (decode step, UNet evaluation), then first-use allocations
 
     def setup(self):
         self.model = full_model()

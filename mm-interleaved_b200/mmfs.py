@@ -125,11 +125,12 @@ class MMFS(nn.Module):
             self._fused = (key, w, b, rtable)
         return self._fused[1:]
 
-    def project_value(self, input_flatten, input_padding_mask=None):
-        """value_proj(input_flatten) as (N, n_img*hw, M, D), cached per input tensor (mmfs.py:165-172)."""
+    def project_value(self, input_flatten, input_padding_mask=None, cache=True):
+        """value_proj(input_flatten) as (N, n_img*hw, M, D), cached per input tensor (mmfs.py:165-172).  ``cache=False``:
+        compute only (callers that keep the result themselves, e.g. ``MMFSNet.prepare``)."""
         w, b = self.value_proj.weight, self.value_proj.bias
         extra = (w.data_ptr(), w._version, b.data_ptr(), b._version)
-        cacheable = input_padding_mask is None and not torch.is_grad_enabled()
+        cacheable = cache and input_padding_mask is None and not torch.is_grad_enabled()
         if cacheable:
             hit = self._value_cache.get(input_flatten, extra)
             if hit is not None:

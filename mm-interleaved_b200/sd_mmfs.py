@@ -137,7 +137,8 @@ class MMFSBlock(nn.Module):
     def project_features(self, ms_feat):
         """value_proj(LayerNorm(ms_feat)) in the sampler's (B, N*HW, heads, D) layout: everything this block derives from
         the feature maps alone (constant over the denoise steps of a loop)."""
-        return self.mmfs.project_value(self.normalised_features(ms_feat))
+        n = self.feat_norm                      # no memoisation here: the caller owns the result (PreparedSDFeatures)
+        return self.mmfs.project_value(ops.layernorm(ms_feat.contiguous(), n.weight, n.bias, n.eps), cache=False)
 
     def forward(self, sample, ms_feat, ms_feat_mask, spatial_shapes, value=None):
         """sample (B, C_q, H, W); ms_feat (B, N, sum(H_l*W_l), C_v); ms_feat_mask (B, N); returns the residual (B, C_q, H, W).

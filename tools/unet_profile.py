@@ -39,6 +39,10 @@ with torch.no_grad():
         unet(x, t, ctx)
         torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=18, max_name_column_width=80))
+    rows = sorted(prof.key_averages(), key=lambda e: -e.count)
+    print(f"kernels per evaluation: {sum(e.count for e in rows)}; by launch count:")
+    for e in rows[:24]:
+        print(f"  n={e.count:4d}  total {e.device_time_total / 1e3:7.2f} ms  avg {e.device_time_total / max(e.count, 1):7.1f} us  {e.key[:90]}")
     print("layer: B Cin Cout H k s | ours us  TF/s | cudnn us")
     for (Cin, Cout, H, k, s) in [(320, 320, 64, 3, 1), (320, 320, 64, 3, 2), (640, 640, 32, 3, 1), (320, 640, 32, 3, 1),
                                  (1280, 1280, 16, 3, 1), (1280, 1280, 8, 3, 1), (2560, 1280, 8, 3, 1), (2560, 1280, 16, 3, 1),
